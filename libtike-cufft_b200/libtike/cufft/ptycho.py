@@ -1,0 +1,407 @@
+"""Ptychography operators and the conjugate-gradient solver, B200-native.
+
+Same public surface as the reference module src/libtike/cufft/ptycho.py
+(`PtychoCuFFT`, `CGPtychoSolver`, context managers, `fwd` / `adj` /
+`adj_probe` on device arrays, the `*_batch` host-array helpers, `run_batch`
+and `run`), re-backed by the fused sm_100a kernels of libptychofft_b200.so:
+
+  * device arrays are torch CUDA tensors (complex64 / float32) instead of CuPy
+    arrays (CuPy is not part of this stack); anything exposing
+    `__cuda_array_interface__` is accepted too;
+  * the ~60 CuPy elementwise / reduction kernels per CG iteration of
+    ptycho.py:308-482 are gone: every pass over the [ptheta, nscan, ndet, ndet]
+    far-field volume is one fused kernel that keeps the far field on chip
+    (ptx_cg_intensity / ptx_cg_grad / ptx_cg_linesearch), and the object- and
+    probe-sized vector updates are the ptx_vec_* kernels.
+
+There is no CPU path: without the CUDA library or a compute-capability-10.x GPU
+the operators raise.
+
+Documented deviations from the reference (see DESIGN.md "Quirks"):
+  Q1  model='poisson' object gradient: the reference raises UnboundLocalError
+      (ptycho.py:357-363 reads `fpsi` before assignment); the evident missing
+      line `fpsi = self.fwd(psi, scan, probe[:, k])` is supplied.
+  Q5  the position-correction block (ptycho.py:398-403) runs only when the
+      solver attribute `position_correction` is True (default False; it is a
+      "next" row).
+  Q9  `_batch` chunks by ptheta (identical at ptheta = 1, the only value the
+      reference's helper is valid for).
+"""
+import ctypes
+import warnings
+
+import numpy as np
+import torch
+
+from libtike.cufft.ptychofft import ptychofft, lib, check, current_stream, PtxError  # noqa: F401
+
+__all__ = ["PtychoCuFFT", "CGPtychoSolver", "line_search_gammas"]
+
+MODELS = {"gaussian": 0, "poisson": 1}
+
+
+def _dev_tensor(x, dtype=None):
+    """torch CUDA view of a device array (torch tensor or __cuda_array_interface__ object)."""
+    if not isinstance(x, torch.Tensor):
+        x = torch.as_tensor(x, device="cuda")
+    if dtype is not None and x.dtype != dtype:
+        raise AssertionError(f"{x.dtype}")
+    return x
+
+
+def _ptr(t):
+    return ctypes.c_void_p(t.data_ptr())
+
+
+class _TorchArrayModule(object):
+    """Minimal stand-in for the reference's `array_module = cp` class attribute (ptycho.py:55)."""
+
+    complex64 = torch.complex64
+    float32 = torch.float32
+
+    @staticmethod
+    def array(x):
+        return torch.as_tensor(np.ascontiguousarray(x)).cuda()
+
+    @staticmethod
+    def zeros(shape, dtype="complex64"):
+        dt = getattr(torch, dtype) if isinstance(dtype, str) else dtype
+        return torch.zeros(*shape, dtype=dt, device="cuda")
+
+    @staticmethod
+    def asnumpy(x):
+        return x.detach().cpu().numpy()
+
+
+class PtychoCuFFT(ptychofft):
+    """Base class for ptychography solvers (reference: ptycho.py:34-162).
+
+    Attributes
+    ----------
+    nscan : int   number of scan positions at each angular view
+    nprb : int    pixel width and height of the probe illumination
+    ndet : int    pixel width and height of the detector
+    ptheta : int  number of angles processed per call (the ctor argument `ntheta`, Q15)
+    n, nz : int   pixel width and height of the reconstructed grid
+    """
+
+    array_module = _TorchArrayModule
+    asnumpy = staticmethod(_TorchArrayModule.asnumpy)
+
+    def __init__(self, nscan, probe_shape, detector_shape, ntheta, nz, n):
+        """Argument order of the reference (ptycho.py:58-60)."""
+        super().__init__(ntheta, nz, n, nscan, detector_shape, probe_shape)
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, type, value, traceback):
+        self.free()
+
+    # ------------------------------------------------------------------ device operators
+    def _probe_arg(self, probe):
+        """(tensor, angle stride) for a [ptheta, P, P] probe, possibly a probe[:, k] view (Q10)."""
+        P = self.nprb
+        if probe.dim() == 3 and probe.stride(2) == 1 and probe.stride(1) == P and \
+                (probe.shape[0] == 1 or probe.stride(0) >= P * P):
+            return probe, (probe.stride(0) if probe.shape[0] > 1 else P * P)
+        probe = probe.contiguous()
+        return probe, P * P
+
+    def fwd(self, psi, scan, probe):
+        """Ptychography transform (FQ), ptycho.py:80-89."""
+        psi = _dev_tensor(psi)
+        scan = _dev_tensor(scan)
+        probe = _dev_tensor(probe)
+        assert psi.dtype == torch.complex64, f"{psi.dtype}"
+        assert scan.dtype == torch.float32, f"{scan.dtype}"
+        assert probe.dtype == torch.complex64, f"{probe.dtype}"
+        psi = psi.contiguous()
+        scan = scan.contiguous()
+        probe, ts = self._probe_arg(probe)
+        # fwd overwrites every element of g, so the reference's zero fill (ptycho.py:85) is dropped
+        farplane = torch.empty((self.ptheta, self.nscan, self.ndet, self.ndet),
+                               dtype=torch.complex64, device=psi.device)
+        ptychofft.fwd(self, farplane.data_ptr(), psi.data_ptr(), scan.data_ptr(),
+                      probe.data_ptr(), ts)
+        return farplane
+
+    def adj(self, farplane, scan, probe):
+        """Adjoint ptychography transform (Q*F*), ptycho.py:97-106."""
+        farplane = _dev_tensor(farplane)
+        scan = _dev_tensor(scan)
+        probe = _dev_tensor(probe)
+        assert farplane.dtype == torch.complex64, f"{farplane.dtype}"
+        assert scan.dtype == torch.float32, f"{scan.dtype}"
+        assert probe.dtype == torch.complex64, f"{probe.dtype}"
+        farplane = farplane.contiguous()
+        scan = scan.contiguous()
+        probe, ts = self._probe_arg(probe)
+        psi = torch.zeros((self.ptheta, self.nz, self.n), dtype=torch.complex64,
+                          device=farplane.device)
+        ptychofft.adj(self, psi.data_ptr(), farplane.data_ptr(), scan.data_ptr(),
+                      probe.data_ptr(), 0, ts)
+        return psi
+
+    def adj_probe(self, farplane, scan, psi):
+        """Adjoint ptychography probe transform (O*F*), object is fixed; ptycho.py:113-123."""
+        farplane = _dev_tensor(farplane)
+        scan = _dev_tensor(scan)
+        psi = _dev_tensor(psi)
+        assert farplane.dtype == torch.complex64, f"{farplane.dtype}"
+        assert scan.dtype == torch.float32, f"{scan.dtype}"
+        assert psi.dtype == torch.complex64, f"{psi.dtype}"
+        farplane = farplane.contiguous()
+        scan = scan.contiguous()
+        psi = psi.contiguous()
+        probe = torch.zeros((self.ptheta, self.nprb, self.nprb), dtype=torch.complex64,
+                            device=farplane.device)
+        ptychofft.adj(self, psi.data_ptr(), farplane.data_ptr(), scan.data_ptr(),
+                      probe.data_ptr(), 1, 0)
+        return probe
+
+    # ------------------------------------------------------------------ host-array helpers
+    def _batch(self, function, output, *inputs):
+        """Host <-> device shuffle, ptycho.py:70-78, chunked by ptheta (Q9).
+
+        Inputs are staged through pinned memory and copied on torch's current
+        stream; the result lands in `output` (a host array) chunk by chunk.
+        """
+        T = self.ptheta
+        ntheta = inputs[0].shape[0]
+        if ntheta % T:
+            raise ValueError(f"leading dimension {ntheta} is not a multiple of ptheta={T}")
+        out_t = torch.from_numpy(output)
+        for ids in range(0, ntheta, T):
+            inputs_gpu = [torch.from_numpy(np.ascontiguousarray(x[ids:ids + T])).cuda(non_blocking=True)
+                          for x in inputs]
+            res = function(*inputs_gpu)
+            out_t[ids:ids + T].copy_(res)
+        return output
+
+    def fwd_ptycho_batch(self, psi, scan, probe):
+        """Batch of ptychography transforms (FQ) on host arrays, ptycho.py:91-95."""
+        data = np.zeros([scan.shape[0], self.nscan, self.ndet, self.ndet], dtype="complex64")
+        return self._batch(self.fwd, data, psi, scan, probe)
+
+    def adj_ptycho_batch(self, farplane, scan, probe):
+        """Batch of adjoint transforms (Q*F*) on host arrays, ptycho.py:108-111."""
+        psi = np.zeros([scan.shape[0], self.nz, self.n], dtype="complex64")
+        return self._batch(self.adj, psi, farplane, scan, probe)
+
+    def adj_ptycho_batch_prb(self, farplane, scan, psi):
+        """Batch of probe adjoints (O*F*) on host arrays, ptycho.py:125-129."""
+        probe = np.zeros([scan.shape[0], self.nprb, self.nprb], dtype="complex64")
+        return self._batch(self.adj_probe, probe, farplane, scan, psi)
+
+    def run(self, data, psi, scan, probe, **kwargs):
+        """Placeholder for a child's solving function (ptycho.py:131-133)."""
+        raise NotImplementedError("Cannot run a base class.")
+
+    def run_batch(self, data, psi, scan, probe, **kwargs):
+        """Run by dividing the work into batches of ptheta angles, ptycho.py:135-162."""
+        assert probe.ndim == 4, "probe needs 4 dimensions, not %d" % probe.ndim
+        psi = psi.copy()
+        probe = probe.copy()
+        T = self.ptheta
+        for k in range(0, scan.shape[0] // T):
+            ids = slice(k * T, (k + 1) * T)
+            psi_gpu = torch.from_numpy(np.ascontiguousarray(psi[ids])).cuda()
+            scan_gpu = torch.from_numpy(np.ascontiguousarray(scan[ids])).cuda()
+            prb_gpu = torch.from_numpy(np.ascontiguousarray(probe[ids])).cuda()
+            data_gpu = torch.from_numpy(np.ascontiguousarray(data[ids])).cuda()
+            result = self.run(data_gpu, psi_gpu, scan_gpu, prb_gpu, **kwargs)
+            psi[ids] = result["psi"].cpu().numpy()
+            probe[ids] = result["probe"].cpu().numpy()
+        return {"psi": psi, "probe": probe}
+
+
+def line_search_gammas(c0, ncand):
+    return [2.0 ** -(c0 + c) for c in range(ncand)]
+
+
+class CGPtychoSolver(PtychoCuFFT):
+    """Solve the ptychography problem using conjugate gradient (reference: ptycho.py:250-488)."""
+
+    #: Q5 -- execute the reference's position-correction block (ptycho.py:398-403)
+    position_correction = False
+    #: step candidates evaluated per fused line-search pass
+    ls_candidates = 4
+
+    @staticmethod
+    def line_search_sqr(f, p1, p2, p3, step_length=1, step_shrink=0.5):
+        """Backtracking line search on f(p1 + g^2 p2 + g p3), verbatim semantics of ptycho.py:253-281."""
+        assert step_shrink > 0 and step_shrink < 1
+        m = 0
+        fp1 = f(p1)
+        while f(p1 + step_length ** 2 * p2 + step_length * p3) > fp1 + step_shrink * m:
+            if step_length < 1e-32:
+                warnings.warn("Line search failed for conjugate gradient.")
+                return 0
+            step_length *= step_shrink
+        return step_length
+
+    # ------------------------------------------------------------------ fused passes
+    def _scalars(self, *vals):
+        return torch.tensor(vals, dtype=torch.float32, device="cuda")
+
+    def _intensity(self, psi, scan, probe, data, inten, model, iscale=None):
+        red = torch.zeros(3, dtype=torch.float64, device=psi.device)
+        sc = self._scalars(iscale) if iscale is not None else None
+        check(lib.ptx_cg_intensity(self._h, _ptr(psi), _ptr(scan), _ptr(probe), probe.shape[1],
+                                   _ptr(data), _ptr(inten) if inten is not None else None,
+                                   _ptr(sc) if sc is not None else None, model, _ptr(red),
+                                   current_stream()))
+        return red
+
+    def _grad(self, what, psi, scan, probe, mode, data, inten, fscale, iscale, gscale, model, out,
+              out_stride=0):
+        sc = self._scalars(fscale, iscale, gscale)
+        check(lib.ptx_cg_grad(self._h, what, _ptr(psi), _ptr(scan), _ptr(probe), probe.shape[1],
+                              mode, _ptr(data), _ptr(inten) if inten is not None else None,
+                              _ptr(sc), model, _ptr(out), out_stride, current_stream()))
+
+    def _line_search(self, obj_a, prb_a, nm_a, m_a, obj_b, prb_b, nm_b, m_b, npairs, scan, data,
+                     p1, model):
+        """Fused line_search_sqr: evaluates `ls_candidates` halvings per pass (ptycho.py:272-281)."""
+        K = int(self.ls_candidates)
+        c0 = 0
+        while True:
+            cost = torch.zeros(1 + K, dtype=torch.float64, device=obj_a.device)
+            check(lib.ptx_cg_linesearch(self._h, _ptr(obj_a), _ptr(prb_a), nm_a, m_a, _ptr(obj_b),
+                                        _ptr(prb_b), nm_b, m_b, npairs, _ptr(scan), _ptr(data),
+                                        _ptr(p1) if p1 is not None else None, model, c0, K,
+                                        _ptr(cost), current_stream()))
+            c = cost.cpu().numpy()
+            for j in range(K):
+                step = 2.0 ** -(c0 + j)
+                if not (c[1 + j] > c[0]):
+                    return step
+                if step < 1e-32:
+                    warnings.warn("Line search failed for conjugate gradient.")
+                    return 0
+            c0 += K
+
+    def _dai_yuan(self, grad, grad0, d, first):
+        red = torch.zeros(3, dtype=torch.float64, device=grad.device)
+        n = grad.numel()
+        if not first:
+            check(lib.ptx_vec_dai_yuan_reduce(_ptr(grad), _ptr(grad0), _ptr(d), n, _ptr(red),
+                                              current_stream()))
+        check(lib.ptx_vec_dai_yuan_update(_ptr(grad), _ptr(grad0), _ptr(d), n, _ptr(red),
+                                          1 if first else 0, current_stream()))
+
+    def _axpy(self, y, x, alpha):
+        a = self._scalars(alpha)
+        check(lib.ptx_vec_axpy(_ptr(y), _ptr(x), y.numel(), _ptr(a), current_stream()))
+
+    def _absmax(self, x):
+        out = torch.zeros(1, dtype=torch.float32, device=x.device)
+        if x.is_contiguous():
+            check(lib.ptx_vec_absmax(_ptr(x), x.numel(), _ptr(out), current_stream()))
+        else:  # probe[:, k] with ptheta > 1: one launch per angle, same accumulator
+            for t in range(x.shape[0]):
+                check(lib.ptx_vec_absmax(_ptr(x[t]), x[t].numel(), _ptr(out), current_stream()))
+        return out
+
+    # ------------------------------------------------------------------ the solver
+    def run(self, data, psi, scan, probe, piter, model="gaussian", recover_prb=False,
+            ortho_prb=False):
+        """Conjugate gradients for ptychography (reference: ptycho.py:283-488).
+
+        Parameters
+        ----------
+        model : str, 'gaussian' or 'poisson' -- the noise model used for the gradient.
+        piter : int -- number of gradient steps.
+        recover_prb : bool -- recover the probe or keep the given one.
+        ortho_prb : accepted and ignored, like the reference (Q8).
+        """
+        assert probe.ndim == 4, "probe needs 4 dimensions, not %d" % probe.ndim
+        if model not in MODELS:
+            raise ValueError("model must be 'gaussian' or 'poisson'")
+        mdl = MODELS[model]
+        data = _dev_tensor(data).contiguous()
+        scan = _dev_tensor(scan).contiguous()
+        psi = _dev_tensor(psi).contiguous().clone()  # the reference rebinds psi (ptycho.py:405)
+        probe_in = _dev_tensor(probe)
+        probe = probe_in if probe_in.is_contiguous() else probe_in.contiguous()  # mutated in place (Q6)
+        assert data.dtype == torch.float32 and psi.dtype == torch.complex64
+        assert probe.dtype == torch.complex64 and scan.dtype == torch.float32
+        T, S, M, P = self.ptheta, self.nscan, probe.shape[1], self.nprb
+        dev = psi.device
+        multi = M > 1
+        inten = torch.empty_like(data) if multi else None
+        sum_data = float(data.sum(dtype=torch.float64)) if mdl == 0 else 0.0
+
+        gradpsi = torch.zeros_like(psi)
+        gradpsi0 = torch.zeros_like(psi)
+        dpsi = torch.zeros_like(psi)
+        # probe-side CG state is kept mode-major [M, T, P, P] so that x[m] is contiguous
+        gradprb = torch.zeros((M, T, P, P), dtype=torch.complex64, device=dev)
+        gradprb0 = torch.zeros_like(gradprb)
+        dprb = torch.zeros_like(gradprb)
+
+        print("# congujate gradient parameters\n"
+              "iteration, step size object, step size probe, function min")  # csv column headers
+        gammaprb = 0
+        for i in range(piter):
+            # 1) object retrieval subproblem with fixed probes (ptycho.py:327-345)
+            red = self._intensity(psi, scan, probe, data, inten, mdl).cpu().numpy()
+            a, b = np.float32(red[0]), np.float32(red[1])
+            s = np.float32(a / b)
+            sc = self._scalars(s)
+            check(lib.ptx_vec_scale(_ptr(probe), probe.numel(), _ptr(sc), current_stream()))
+            iscale = float(s) * float(s)                     # absfpsi *= (a/b)**2
+            if i % 32 == 0:  # cost of this iteration's absfpsi, printed below (ptycho.py:481-482)
+                if mdl == 0:
+                    fmin = float(s) ** 2 * red[1] - 2.0 * float(s) * red[0] + sum_data
+                else:
+                    fmin = float(self._intensity(psi, scan, probe, data, None, mdl)[2])
+            # gradient (ptycho.py:346-363)
+            gradpsi.zero_()
+            for k in range(M):
+                pmax = float(self._absmax(probe[:, k]))
+                fscale = float(np.float32(b / a)) if mdl == 0 else 1.0
+                self._grad(0, psi, scan, probe, k, data, inten, fscale, iscale,
+                           1.0 / (pmax * pmax), mdl, gradpsi)
+            # Dai-Yuan direction (ptycho.py:364-372)
+            self._dai_yuan(gradpsi, gradpsi0, dpsi, i == 0)
+            # line search (ptycho.py:374-393)
+            gammapsi = 0.5 * self._line_search(psi, probe, M, 0, dpsi, probe, M, 0, M, scan, data,
+                                               None, mdl)
+            if self.position_correction and i > 0:
+                raise NotImplementedError(
+                    "position correction (ptycho.py:398-403) is a 'next' row and not built yet")
+            # update psi (ptycho.py:405)
+            self._axpy(psi, dpsi, gammapsi)
+
+            if recover_prb:
+                for m in range(M):
+                    # 2) probe retrieval subproblem with fixed object (ptycho.py:420-441)
+                    if multi:
+                        self._intensity(psi, scan, probe, data, inten, mdl)
+                    psimax = float(self._absmax(psi))
+                    gscale = 1.0 / (psimax * psimax) / S
+                    if mdl == 0:
+                        gscale *= M
+                    gradprb[m].zero_()
+                    self._grad(1, psi, scan, probe, m, data, inten, 1.0, 1.0, gscale, mdl,
+                               gradprb[m], P * P)
+                    # Dai-Yuan direction (ptycho.py:442-450)
+                    self._dai_yuan(gradprb[m], gradprb0[m], dprb[m], i == 0)
+                    # line search (ptycho.py:451-461)
+                    gammaprb = 0.5 * self._line_search(psi, probe, M, m, psi, dprb[m], 1, 0, 1,
+                                                       scan, data, inten, mdl)
+                    # update probe (ptycho.py:463)
+                    if T == 1:
+                        self._axpy(probe[0, m], dprb[m, 0], gammaprb)
+                    else:
+                        for t in range(T):
+                            self._axpy(probe[t, m], dprb[m, t], gammaprb)
+            # check convergence (ptycho.py:474-482)
+            if i % 32 == 0:
+                print("%4d, %.3e, %.3e, %.7e" % (i, gammapsi, gammaprb, fmin))
+
+        if probe is not probe_in:
+            probe_in.copy_(probe)
+        return {"psi": psi, "probe": probe_in}

@@ -1,0 +1,284 @@
+"""GPU oracle: the reference's own compiled CUDA/cuFFT code + a torch restatement of its Python layer.
+
+TEST INFRASTRUCTURE, NOT PRODUCT CODE.  Only tests/, tests/golden/make_golden.py,
+__graft_entry__.smoke() and bench.py's reference arm may import this module.
+
+* `RefPtychoFFT` drives oracle/_ref/libptychofft_ref.so, i.e. the UNMODIFIED
+  /root/reference/src/cuda/ptychofft.cu + kernels.cu compiled where they lie by
+  oracle/Makefile (cuFFT 11.4 from CUDA 12.9), through raw device pointers, as
+  src/libtike/cufft/ptycho.py:80-123 does with CuPy's `.data.ptr`.
+* `RefCGPtychoSolver.run` restates src/libtike/cufft/ptycho.py:283-488 statement by
+  statement with `cp.` -> `torch.` (CuPy is not installed in this image, so the
+  reference's Python layer cannot be imported -- SURVEY.md section 8c).  Deviations:
+    Q1  the missing `fpsi = self.fwd(...)` line of the Poisson object branch
+        (ptycho.py:357-363) is added (the reference raises UnboundLocalError);
+    Q5  the position-correction block (ptycho.py:398-403) is behind
+        `position_correction` (default False, the primary parity configuration);
+    Q7  the dead `sfpsi` recompute (ptycho.py:476-480) is skipped;
+    Q10 `probe[:, k]` views are made contiguous before their pointer is taken (the
+        reference passes the view's base pointer, which is only right for ptheta = 1).
+"""
+import ctypes
+import os
+import warnings
+
+import numpy as np
+import torch
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+_LIB = os.path.join(_HERE, "_ref", "libptychofft_ref.so")
+
+
+def available():
+    return os.path.exists(_LIB)
+
+
+_lib = None
+
+
+def _load():
+    global _lib
+    if _lib is None:
+        lib = ctypes.CDLL(_LIB)
+        sz, vp = ctypes.c_size_t, ctypes.c_void_p
+        lib.ref_create.restype = vp
+        lib.ref_create.argtypes = [sz] * 6
+        lib.ref_fwd.argtypes = [vp, sz, sz, sz, sz]
+        lib.ref_adj.argtypes = [vp, sz, sz, sz, sz, ctypes.c_int]
+        lib.ref_free.argtypes = [vp]
+        lib.ref_destroy.argtypes = [vp]
+        lib.ref_last_cuda_error.restype = ctypes.c_int
+        lib.ref_device_sync.restype = ctypes.c_int
+        _lib = lib
+    return _lib
+
+
+class RefPtychoFFT(object):
+    """PtychoCuFFT of the reference (ptycho.py:34-129) on torch tensors, legacy default stream."""
+
+    def __init__(self, nscan, probe_shape, detector_shape, ntheta, nz, n):
+        self._lib = _load()
+        self.ptheta, self.nz, self.n = ntheta, nz, n
+        self.nscan, self.ndet, self.nprb = nscan, detector_shape, probe_shape
+        self._h = ctypes.c_void_p(self._lib.ref_create(ntheta, nz, n, nscan, detector_shape,
+                                                       probe_shape))
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *exc):
+        self.free()
+
+    def free(self):
+        if self._h:
+            self._lib.ref_free(self._h)
+
+    def __del__(self):
+        try:
+            if self._h:
+                self._lib.ref_destroy(self._h)
+                self._h = None
+        except Exception:
+            pass
+
+    def _check(self):
+        err = self._lib.ref_last_cuda_error()
+        if err:
+            raise RuntimeError("reference CUDA error %d" % err)
+
+    def fwd(self, psi, scan, probe):
+        assert psi.dtype == torch.complex64 and scan.dtype == torch.float32
+        assert probe.dtype == torch.complex64
+        psi, scan, probe = psi.contiguous(), scan.contiguous(), probe.contiguous()
+        farplane = torch.zeros([self.ptheta, self.nscan, self.ndet, self.ndet],
+                               dtype=torch.complex64, device="cuda")
+        self._lib.ref_fwd(self._h, farplane.data_ptr(), psi.data_ptr(), scan.data_ptr(),
+                          probe.data_ptr())
+        self._check()
+        return farplane
+
+    def adj(self, farplane, scan, probe):
+        farplane, scan, probe = farplane.contiguous(), scan.contiguous(), probe.contiguous()
+        psi = torch.zeros([self.ptheta, self.nz, self.n], dtype=torch.complex64, device="cuda")
+        self._lib.ref_adj(self._h, psi.data_ptr(), farplane.data_ptr(), scan.data_ptr(),
+                          probe.data_ptr(), 0)
+        self._check()
+        return psi
+
+    def adj_probe(self, farplane, scan, psi):
+        farplane, scan, psi = farplane.contiguous(), scan.contiguous(), psi.contiguous()
+        probe = torch.zeros([self.ptheta, self.nprb, self.nprb], dtype=torch.complex64,
+                            device="cuda")
+        self._lib.ref_adj(self._h, psi.data_ptr(), farplane.data_ptr(), scan.data_ptr(),
+                          probe.data_ptr(), 1)
+        self._check()
+        return probe
+
+    # host-array helpers exactly as the reference runs them: one angle per call,
+    # pageable H2D (cp.array) and a blocking D2H (.get()) per angle (ptycho.py:70-78)
+    def _batch(self, function, output, *inputs):
+        for ids in range(0, inputs[0].shape[0]):
+            inputs_gpu = [torch.from_numpy(np.ascontiguousarray(x[ids:ids + 1])).cuda()
+                          for x in inputs]
+            output[ids] = function(*inputs_gpu).cpu().numpy()
+        return output
+
+    def fwd_ptycho_batch(self, psi, scan, probe):
+        data = np.zeros([scan.shape[0], self.nscan, self.ndet, self.ndet], dtype="complex64")
+        return self._batch(self.fwd, data, psi, scan, probe)
+
+    def adj_ptycho_batch(self, farplane, scan, probe):
+        psi = np.zeros([scan.shape[0], self.nz, self.n], dtype="complex64")
+        return self._batch(self.adj, psi, farplane, scan, probe)
+
+    def adj_ptycho_batch_prb(self, farplane, scan, psi):
+        probe = np.zeros([scan.shape[0], self.nprb, self.nprb], dtype="complex64")
+        return self._batch(self.adj_probe, probe, farplane, scan, psi)
+
+
+class RefCGPtychoSolver(RefPtychoFFT):
+    """torch restatement of CGPtychoSolver (ptycho.py:250-488)."""
+
+    position_correction = False
+
+    @staticmethod
+    def line_search_sqr(f, p1, p2, p3, step_length=1, step_shrink=0.5, trials=None):
+        assert step_shrink > 0 and step_shrink < 1
+        m = 0
+        fp1 = f(p1)
+        n = 1
+        while f(p1 + step_length ** 2 * p2 + step_length * p3) > fp1 + step_shrink * m:
+            if step_length < 1e-32:
+                warnings.warn("Line search failed for conjugate gradient.")
+                return 0
+            step_length *= step_shrink
+            n += 1
+        if trials is not None:
+            trials.append(n)
+        return step_length
+
+    def run(self, data, psi, scan, probe, piter, model="gaussian", recover_prb=False,
+            ortho_prb=False, history=None, verbose=True):
+        assert probe.ndim == 4, "probe needs 4 dimensions, not %d" % probe.ndim
+
+        def minf(fpsi):
+            if model == "gaussian":
+                f = torch.linalg.norm(torch.sqrt(torch.abs(fpsi)) - torch.sqrt(data)) ** 2
+            elif model == "poisson":
+                f = torch.sum(torch.abs(fpsi) - data * torch.log(torch.abs(fpsi) + 1e-32))
+            return f
+
+        dprb = 0
+        dpsi = 0
+        gradprb0 = 0
+        gradpsi0 = 0
+        if verbose:
+            print("# congujate gradient parameters\n"
+                  "iteration, step size object, step size probe, function min")
+        gammaprb = 0
+        trials = []
+        for i in range(piter):
+            absfpsi = data * 0
+            for k in range(probe.shape[1]):
+                tmp = self.fwd(psi, scan, probe[:, k])
+                absfpsi += torch.abs(tmp) ** 2
+            a = torch.sum(torch.sqrt(absfpsi * data))
+            b = torch.sum(absfpsi)
+            probe *= (a / b)
+            absfpsi *= (a / b) ** 2
+            gradpsi = torch.zeros([self.ptheta, self.nz, self.n], dtype=torch.complex64,
+                                  device="cuda")
+            if model == "gaussian":
+                for k in range(probe.shape[1]):
+                    fpsi = self.fwd(psi, scan, probe[:, k]) * (b / a)
+                    gradpsi += self.adj(
+                        fpsi - torch.sqrt(data) * fpsi / (torch.sqrt(absfpsi) + 1e-32),
+                        scan, probe[:, k]) / (torch.max(torch.abs(probe[:, k])) ** 2)
+            elif model == "poisson":
+                for k in range(probe.shape[1]):
+                    fpsi = self.fwd(psi, scan, probe[:, k])  # Q1
+                    gradpsi += self.adj(
+                        fpsi - data * fpsi / (absfpsi + 1e-32),
+                        scan, probe[:, k]) / (torch.max(torch.abs(probe[:, k])) ** 2)
+            if i == 0:
+                dpsi = -gradpsi
+            else:
+                dpsi = -gradpsi + (
+                    torch.linalg.norm(gradpsi) ** 2 /
+                    (torch.sum(torch.conj(dpsi) * (gradpsi - gradpsi0))) * dpsi)
+            gradpsi0 = gradpsi
+            p1 = data * 0
+            p2 = data * 0
+            p3 = data * 0
+            for k in range(probe.shape[1]):
+                tmp1 = self.fwd(psi, scan, probe[:, k])
+                tmp2 = self.fwd(dpsi, scan, probe[:, k])
+                p1 += torch.abs(tmp1) ** 2
+                p2 += torch.abs(tmp2) ** 2
+                p3 += 2 * (tmp1.real * tmp2.real + tmp1.imag * tmp2.imag)
+            gammapsi = 0.5 * self.line_search_sqr(minf, p1, p2, p3, trials=trials)
+            if self.position_correction and i > 0:
+                raise NotImplementedError("position correction restatement: next round")
+            psi = psi + gammapsi * dpsi
+
+            if recover_prb:
+                if i == 0:
+                    gradprb = probe * 0
+                    gradprb0 = probe * 0
+                    dprb = probe * 0
+                for m in range(0, probe.shape[1]):
+                    fprb = self.fwd(psi, scan, probe[:, m])
+                    absfprb = data * 0
+                    for k in range(probe.shape[1]):
+                        tmp = self.fwd(psi, scan, probe[:, k])
+                        absfprb += torch.abs(tmp) ** 2
+                    if model == "gaussian":
+                        gradprb[:, m] = self.adj_probe(
+                            fprb - torch.sqrt(data) * fprb / (torch.sqrt(absfprb) + 1e-32),
+                            scan, psi) / torch.max(torch.abs(psi)) ** 2 / self.nscan * probe.shape[1]
+                    elif model == "poisson":
+                        gradprb[:, m] = self.adj_probe(
+                            fprb - data * fprb / (absfprb + 1e-32),
+                            scan, psi) / torch.max(torch.abs(psi)) ** 2 / self.nscan
+                    if i == 0:
+                        dprb[:, m] = -gradprb[:, m]
+                    else:
+                        dprb[:, m] = -gradprb[:, m] + (
+                            torch.linalg.norm(gradprb[:, m]) ** 2 /
+                            (torch.sum(torch.conj(dprb[:, m]) * (gradprb[:, m] - gradprb0[:, m])))
+                            * dprb[:, m])
+                    gradprb0[:, m] = gradprb[:, m]
+                    p1 = data * 0
+                    p2 = data * 0
+                    p3 = data * 0
+                    for k in range(probe.shape[1]):
+                        tmp1 = self.fwd(psi, scan, probe[:, k])
+                        p1 += torch.abs(tmp1) ** 2
+                    tmp1 = self.fwd(psi, scan, probe[:, m])
+                    tmp2 = self.fwd(psi, scan, dprb[:, m])
+                    p2 = torch.abs(tmp2) ** 2
+                    p3 = 2 * (tmp1.real * tmp2.real + tmp1.imag * tmp2.imag)
+                    gammaprb = 0.5 * self.line_search_sqr(minf, p1, p2, p3, step_length=1,
+                                                          trials=trials)
+                    probe[:, m] = probe[:, m] + gammaprb * dprb[:, m]
+            if history is not None:
+                history.append((i, float(gammapsi), float(gammaprb), float(minf(absfpsi))))
+            if np.mod(i, 32) == 0 and verbose:
+                print("%4d, %.3e, %.3e, %.7e" % (i, gammapsi, gammaprb, minf(absfpsi)))
+        self.last_trials = trials
+        return {"psi": psi, "probe": probe}
+
+    def run_batch(self, data, psi, scan, probe, **kwargs):
+        """ptycho.py:135-162"""
+        assert probe.ndim == 4
+        psi = psi.copy()
+        probe = probe.copy()
+        for k in range(0, scan.shape[0] // self.ptheta):
+            ids = np.arange(k * self.ptheta, (k + 1) * self.ptheta)
+            psi_gpu = torch.from_numpy(psi[ids]).cuda()
+            scan_gpu = torch.from_numpy(scan[ids]).cuda()
+            prb_gpu = torch.from_numpy(probe[ids]).cuda()
+            data_gpu = torch.from_numpy(data[ids]).cuda()
+            result = self.run(data_gpu, psi_gpu, scan_gpu, prb_gpu, **kwargs)
+            psi[ids], probe[ids] = result["psi"].cpu().numpy(), result["probe"].cpu().numpy()
+        return {"psi": psi, "probe": probe}
