@@ -8,6 +8,7 @@
 #include <cuda_runtime.h>
 #include <stdarg.h>
 #include <stdio.h>
+#include <stdlib.h>
 #include <string.h>
 
 #include <atomic>
@@ -65,11 +66,26 @@ __device__ __forceinline__ void smem_setup(unsigned char* raw, const float2* tw_
   __syncthreads();
 }
 
+// Square root / division without the IEEE slow-path subroutine calls: MUFU.RSQ / MUFU.RCP plus one
+// Newton step, accurate to ~1 ulp for the non-negative, normal-range inputs of this path.
+__device__ __forceinline__ float fsqrt(float x) {
+  if (x < 1e-35f) return 0.f;
+  const float r = rsqrtf(x);
+  float s = x * r;                       // ~sqrt(x)
+  s = fmaf(fmaf(-s, s, x), 0.5f * r, s); // one Newton step
+  return s;
+}
+__device__ __forceinline__ float fdiv(float a, float b) {
+  const float r = __frcp_rn(b);
+  const float q = a * r;
+  return fmaf(fmaf(-q, b, a), r, q);
+}
+
 // minimisation functional per pixel (ptycho.py:308-314), x = intensity estimate, d = data
 template <int MODEL>
 __device__ __forceinline__ float minf_px(float x, float d, float sqd) {
   if (MODEL == PTX_MODEL_GAUSSIAN) {
-    const float r = sqrtf(fabsf(x)) - sqd;
+    const float r = fsqrt(fabsf(x)) - sqd;
     return r * r;
   } else {
     const float ax = fabsf(x);
@@ -265,9 +281,9 @@ __global__ void __launch_bounds__(P::NT) k_intensity(const PassArgs a) {
     for (int e = 0; e < P::E; ++e) {
       const int k = spec_index<P>(e, xf2, yf2);
       const float dd = __ldg(d + k);
-      sa += sqrtf(I[e] * dd);
+      sa += fsqrt(I[e] * dd);
       sb += I[e];
-      scost += minf_px<MODEL>(I[e] * iscale, dd, sqrtf(dd));
+      scost += minf_px<MODEL>(I[e] * iscale, dd, fsqrt(dd));
       if (io) io[k] = I[e];
     }
     acc[0] += (double)sa;
@@ -323,9 +339,9 @@ __global__ void __launch_bounds__(P::NT) k_grad(const PassArgs a) {
       const float I = ii ? __ldg(ii + k) * iscale : (v[e].x * v[e].x + v[e].y * v[e].y);
       float f;
       if (MODEL == PTX_MODEL_GAUSSIAN)
-        f = fscale * (1.f - sqrtf(dd) / (sqrtf(I) + 1e-32f));
+        f = fscale * (1.f - fdiv(fsqrt(dd), fsqrt(I) + 1e-32f));
       else
-        f = fscale * (1.f - dd / (I + 1e-32f));
+        f = fscale * (1.f - fdiv(dd, I + 1e-32f));
       v[e].x *= f;
       v[e].y *= f;
     }
@@ -417,7 +433,7 @@ __global__ void __launch_bounds__(P::NT) k_linesearch(const PassArgs a) {
         if (j + 1 == a.npairs) {
           const int k = spec_index<P>(e, xf2, yf2);
           const float dd = __ldg(d + k);
-          const float sqd = sqrtf(dd);
+          const float sqd = fsqrt(dd);
           if (p1in) q1 = __ldg(p1in + k);
           cost[0] += minf_px<MODEL>(q1, dd, sqd);
           float gam = exp2f(-(float)a.c0);
@@ -573,15 +589,25 @@ static int plan_init(ptx_plan* p) {
   return PTX_OK;
 }
 
+static bool debug_sync() {
+  static const bool on = getenv("PTX_DEBUG_SYNC") != nullptr;
+  return on;
+}
+
 template <class P, class K>
-static int launch(ptx_plan* p, K kernel, const PassArgs& a, cudaStream_t st) {
+static int launch_named(ptx_plan* p, K kernel, const char* name, const PassArgs& a, cudaStream_t st) {
   const int npat = a.g.T * a.g.S;
   const int grid = npat < p->grid ? npat : p->grid;
   kernel<<<grid, P::NT, Smem<P>::BYTES, st>>>(a);
   g_launches.fetch_add(1);
   CUDA_TRY(cudaGetLastError());
+  if (debug_sync()) {  // PTX_DEBUG_SYNC=1: attribute asynchronous faults to the kernel that raised them
+    cudaError_t e = cudaStreamSynchronize(st);
+    if (e != cudaSuccess) return fail(PTX_ECUDA, "%s (grid %d): %s", name, grid, cudaGetErrorString(e));
+  }
   return PTX_OK;
 }
+#define LAUNCH(st, a, ...) launch_named<PL>(p, __VA_ARGS__, #__VA_ARGS__, a, st)
 
 static int check_plan(const ptx_plan* p) {
   if (!p) return fail(PTX_EINVAL, "null plan");
@@ -724,7 +750,7 @@ int ptx_fwd(ptx_plan* p, void* g, const void* f, const void* scan, const void* p
   a.scan = (const float2*)scan;
   a.prb = (const float2*)prb;
   a.prb_ts = prb_angle_stride ? prb_angle_stride : p->nprb * p->nprb;
-  DISPATCH_L(p, return (launch<PL>(p, k_fwd<PL>, a, (cudaStream_t)stream)));
+  DISPATCH_L(p, return (LAUNCH((cudaStream_t)stream, a, k_fwd<PL>)));
   return PTX_OK;
 }
 
@@ -765,12 +791,12 @@ int ptx_adj(ptx_plan* p, void* f, const void* g, const void* scan, void* prb,
     a.grad = (float2*)f;
     a.prb = (const float2*)prb;
     a.prb_ts = ts;
-    DISPATCH_L(p, return (launch<PL>(p, k_adj<PL, 0>, a, (cudaStream_t)stream)));
+    DISPATCH_L(p, return (LAUNCH((cudaStream_t)stream, a, k_adj<PL, 0>)));
   } else {
     a.psi = (const float2*)f;
     a.grad = (float2*)prb;
     a.grad_ts = ts;
-    DISPATCH_L(p, return (launch<PL>(p, k_adj<PL, 1>, a, (cudaStream_t)stream)));
+    DISPATCH_L(p, return (LAUNCH((cudaStream_t)stream, a, k_adj<PL, 1>)));
   }
   return PTX_OK;
 }
@@ -794,9 +820,9 @@ int ptx_cg_intensity(ptx_plan* p, const void* psi, const void* scan, const void*
   a.sc = iscale_dev;
   a.red = red;
   if (model == PTX_MODEL_GAUSSIAN) {
-    DISPATCH_L(p, return (launch<PL>(p, k_intensity<PL, 0>, a, (cudaStream_t)stream)));
+    DISPATCH_L(p, return (LAUNCH((cudaStream_t)stream, a, k_intensity<PL, 0>)));
   } else if (model == PTX_MODEL_POISSON) {
-    DISPATCH_L(p, return (launch<PL>(p, k_intensity<PL, 1>, a, (cudaStream_t)stream)));
+    DISPATCH_L(p, return (LAUNCH((cudaStream_t)stream, a, k_intensity<PL, 1>)));
   }
   return fail(PTX_EINVAL, "unknown model %d", model);
 }
@@ -822,11 +848,11 @@ int ptx_cg_grad(ptx_plan* p, int what, const void* psi, const void* scan, const 
   a.grad_ts = grad_angle_stride ? grad_angle_stride : pp;
   cudaStream_t st = (cudaStream_t)stream;
   if (model == PTX_MODEL_GAUSSIAN) {
-    if (what == 0) { DISPATCH_L(p, return (launch<PL>(p, k_grad<PL, 0, 0>, a, st))); }
-    else { DISPATCH_L(p, return (launch<PL>(p, k_grad<PL, 0, 1>, a, st))); }
+    if (what == 0) { DISPATCH_L(p, return (LAUNCH(st, a, k_grad<PL, 0, 0>))); }
+    else { DISPATCH_L(p, return (LAUNCH(st, a, k_grad<PL, 0, 1>))); }
   } else if (model == PTX_MODEL_POISSON) {
-    if (what == 0) { DISPATCH_L(p, return (launch<PL>(p, k_grad<PL, 1, 0>, a, st))); }
-    else { DISPATCH_L(p, return (launch<PL>(p, k_grad<PL, 1, 1>, a, st))); }
+    if (what == 0) { DISPATCH_L(p, return (LAUNCH(st, a, k_grad<PL, 1, 0>))); }
+    else { DISPATCH_L(p, return (LAUNCH(st, a, k_grad<PL, 1, 1>))); }
   }
   return fail(PTX_EINVAL, "unknown model %d", model);
 }
@@ -860,9 +886,9 @@ int ptx_cg_linesearch(ptx_plan* p, const void* obj_a, const void* prb_a, int nmo
   a.red = cost;
   cudaStream_t st = (cudaStream_t)stream;
   if (model == PTX_MODEL_GAUSSIAN) {
-    DISPATCH_L(p, return (launch<PL>(p, k_linesearch<PL, 0>, a, st)));
+    DISPATCH_L(p, return (LAUNCH(st, a, k_linesearch<PL, 0>)));
   } else if (model == PTX_MODEL_POISSON) {
-    DISPATCH_L(p, return (launch<PL>(p, k_linesearch<PL, 1>, a, st)));
+    DISPATCH_L(p, return (LAUNCH(st, a, k_linesearch<PL, 1>)));
   }
   return fail(PTX_EINVAL, "unknown model %d", model);
 }

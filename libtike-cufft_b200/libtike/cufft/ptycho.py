@@ -227,6 +227,9 @@ class CGPtychoSolver(PtychoCuFFT):
     position_correction = False
     #: step candidates evaluated per fused line-search pass
     ls_candidates = 4
+    #: diagnostics hook used by the parity tests: a list of raw line-search results, consumed in call
+    #: order, that override the solver's own decisions (the costs are still evaluated and logged)
+    _forced_steps = None
 
     @staticmethod
     def line_search_sqr(f, p1, p2, p3, step_length=1, step_shrink=0.5):
@@ -266,16 +269,20 @@ class CGPtychoSolver(PtychoCuFFT):
         """Fused line_search_sqr: evaluates `ls_candidates` halvings per pass (ptycho.py:272-281)."""
         K = int(self.ls_candidates)
         c0 = 0
+        forced = self._forced_steps.pop(0) if self._forced_steps else None
         while True:
-            cost = torch.zeros(1 + K, dtype=torch.float64, device=obj_a.device)
+            cost = torch.zeros(9, dtype=torch.float64, device=obj_a.device)  # kernel reduces 1 + 8 slots
             check(lib.ptx_cg_linesearch(self._h, _ptr(obj_a), _ptr(prb_a), nm_a, m_a, _ptr(obj_b),
                                         _ptr(prb_b), nm_b, m_b, npairs, _ptr(scan), _ptr(data),
                                         _ptr(p1) if p1 is not None else None, model, c0, K,
                                         _ptr(cost), current_stream()))
             c = cost.cpu().numpy()
+            self.ls_log.append((c0, c[:1 + K].copy()))
+            if forced is not None and (forced == 0 or forced >= 2.0 ** -(c0 + K - 1)):
+                return forced
             for j in range(K):
                 step = 2.0 ** -(c0 + j)
-                if not (c[1 + j] > c[0]):
+                if forced is None and not (c[1 + j] > c[0]):
                     return step
                 if step < 1e-32:
                     warnings.warn("Line search failed for conjugate gradient.")
@@ -302,6 +309,83 @@ class CGPtychoSolver(PtychoCuFFT):
         else:  # probe[:, k] with ptheta > 1: one launch per angle, same accumulator
             for t in range(x.shape[0]):
                 check(lib.ptx_vec_absmax(_ptr(x[t]), x[t].numel(), _ptr(out), current_stream()))
+        return out
+
+    # ------------------------------------------------------------------ fused gradient, host arrays
+    def grad_ptycho_batch(self, data, psi, scan, probe, model="gaussian"):
+        """Object gradient of the data-fit cost for a batch of angles given as HOST arrays.
+
+        Per angle chunk of `ptheta`: sum_k Q_k* F* [ F Q_k psi * (1 - sqrt(d)/(sqrt(I)+1e-32)) ]
+        (gaussian; `d/(I+1e-32)` for poisson), I = sum_k |F Q_k psi|^2 -- the forward and adjoint
+        chain of ptycho.py:347-363 without the CG normalisations -- computed by ONE fused kernel
+        per mode with the far field kept on chip.  Inputs are staged through pinned buffers on two
+        streams so that the H2D copy of chunk i+1 and the D2H copy of chunk i-1 overlap the
+        kernels of chunk i.  Returns a host array [ntheta, nz, n] complex64.
+        """
+        assert probe.ndim == 4, "probe needs 4 dimensions, not %d" % probe.ndim
+        mdl = MODELS[model]
+        T, M = self.ptheta, probe.shape[1]
+        ntheta = scan.shape[0]
+        if ntheta % T:
+            raise ValueError(f"leading dimension {ntheta} is not a multiple of ptheta={T}")
+        out = np.empty((ntheta, self.nz, self.n), dtype=np.complex64)
+        dev = torch.device("cuda", torch.cuda.current_device())
+        st = getattr(self, "_pipe", None)
+        if st is None or st["M"] != M:
+            def pin(shape, dtype):
+                return torch.empty(shape, dtype=dtype).pin_memory()
+            st = {"M": M, "streams": [torch.cuda.Stream(), torch.cuda.Stream()], "slots": []}
+            for _ in range(2):
+                st["slots"].append({
+                    "h": (pin((T, self.nscan, self.ndet, self.ndet), torch.float32),
+                          pin((T, self.nz, self.n), torch.complex64),
+                          pin((T, self.nscan, 2), torch.float32),
+                          pin((T, M, self.nprb, self.nprb), torch.complex64)),
+                    "d": (torch.empty((T, self.nscan, self.ndet, self.ndet), dtype=torch.float32, device=dev),
+                          torch.empty((T, self.nz, self.n), dtype=torch.complex64, device=dev),
+                          torch.empty((T, self.nscan, 2), dtype=torch.float32, device=dev),
+                          torch.empty((T, M, self.nprb, self.nprb), dtype=torch.complex64, device=dev)),
+                    "g": torch.empty((T, self.nz, self.n), dtype=torch.complex64, device=dev),
+                    "gh": pin((T, self.nz, self.n), torch.complex64),
+                    "inten": (torch.empty((T, self.nscan, self.ndet, self.ndet), dtype=torch.float32,
+                                          device=dev) if M > 1 else None),
+                    "done": None, "ids": None})
+            self._pipe = st
+        nchunk = ntheta // T
+
+        def drain(slot):
+            if slot["done"] is not None:
+                slot["done"].synchronize()
+                out[slot["ids"]] = slot["gh"].numpy()
+                slot["done"] = None
+
+        for c in range(nchunk):
+            slot, stream = st["slots"][c % 2], st["streams"][c % 2]
+            drain(slot)  # the pinned buffers of this slot are free again
+            ids = slice(c * T, (c + 1) * T)
+            srcs = []
+            for hbuf, src in zip(slot["h"], (data, psi, scan, probe)):
+                t = torch.from_numpy(np.ascontiguousarray(src[ids]))
+                if not t.is_pinned():  # pageable caller memory is staged; pinned memory is DMA'd as is
+                    hbuf.copy_(t)
+                    t = hbuf
+                srcs.append(t)
+            with torch.cuda.stream(stream):
+                for t, dbuf in zip(srcs, slot["d"]):
+                    dbuf.copy_(t, non_blocking=True)
+                d_data, d_psi, d_scan, d_prb = slot["d"]
+                slot["g"].zero_()
+                if M > 1:
+                    self._intensity(d_psi, d_scan, d_prb, d_data, slot["inten"], mdl)
+                for k in range(M):
+                    self._grad(0, d_psi, d_scan, d_prb, k, d_data, slot["inten"], 1.0, 1.0, 1.0, mdl,
+                               slot["g"])
+                slot["gh"].copy_(slot["g"], non_blocking=True)
+                slot["done"] = torch.cuda.Event()
+                slot["done"].record(stream)
+                slot["ids"] = ids
+        for slot in st["slots"]:
+            drain(slot)
         return out
 
     # ------------------------------------------------------------------ the solver
@@ -344,6 +428,8 @@ class CGPtychoSolver(PtychoCuFFT):
         print("# congujate gradient parameters\n"
               "iteration, step size object, step size probe, function min")  # csv column headers
         gammaprb = 0
+        self.history = []  # (iteration, step size object, step size probe) -- diagnostics only
+        self.ls_log = []   # (first candidate exponent, [f(0), f(2^-c0), ...]) per fused pass
         for i in range(piter):
             # 1) object retrieval subproblem with fixed probes (ptycho.py:327-345)
             red = self._intensity(psi, scan, probe, data, inten, mdl).cpu().numpy()
@@ -398,6 +484,7 @@ class CGPtychoSolver(PtychoCuFFT):
                     else:
                         for t in range(T):
                             self._axpy(probe[t, m], dprb[m, t], gammaprb)
+            self.history.append((i, gammapsi, gammaprb))
             # check convergence (ptycho.py:474-482)
             if i % 32 == 0:
                 print("%4d, %.3e, %.3e, %.7e" % (i, gammapsi, gammaprb, fmin))

@@ -34,6 +34,24 @@ F32 = np.float32
 C64 = np.complex64
 
 
+class float64_arithmetic(object):
+    """Context manager: run the restatement in float64 / complex128 instead of the reference's
+    float32 / complex64.  Used by the parity tests as the exact answer against which the rounding
+    error of BOTH the reference's cuFFT path and the sm_100a kernels is measured where the
+    reference's formula is ill-conditioned (Poisson gradient on noisy data: d * F / (|F|^2 + 1e-32)
+    amplifies the fp32 FFT rounding error at weak-signal pixels that recorded a photon)."""
+
+    def __enter__(self):
+        global F32, C64
+        self._saved = (F32, C64)
+        F32, C64 = np.float64, np.complex128
+        return self
+
+    def __exit__(self, *exc):
+        global F32, C64
+        F32, C64 = self._saved
+
+
 def _split_scan(scan_t):
     """modff split of one angle's scan positions (kernels.cu:27-28, 39).
 
@@ -163,9 +181,16 @@ def adj_probe(g, scan, psi, nprb, workers=-1):
 # CG solver (ptycho.py:250-488), float32 arithmetic like CuPy's.
 # ----------------------------------------------------------------------------
 
-def line_search_sqr(f, p1, p2, p3, step_length=1, step_shrink=0.5):
-    """ptycho.py:253-281 -- backtracking on f(p1 + g^2 p2 + g p3), m = 0."""
+def line_search_sqr(f, p1, p2, p3, step_length=1, step_shrink=0.5, forced=None):
+    """ptycho.py:253-281 -- backtracking on f(p1 + g^2 p2 + g p3), m = 0.
+
+    `forced` (diagnostics): a list of reference decisions consumed in call order; when given the
+    search result is overridden so that near-tie decisions (fp32 summation noise) cannot fork the
+    trajectory of a long parity run.
+    """
     assert 0 < step_shrink < 1
+    if forced:
+        return forced.pop(0)
     m = 0
     fp1 = f(p1)
     while f(p1 + F32(step_length ** 2) * p2 + F32(step_length) * p3) > fp1 + step_shrink * m:
@@ -177,7 +202,7 @@ def line_search_sqr(f, p1, p2, p3, step_length=1, step_shrink=0.5):
 
 
 def cg_run(data, psi, scan, probe, piter, model="gaussian", recover_prb=False,
-           ndet=None, verbose=False, history=None):
+           ndet=None, verbose=False, history=None, forced_steps=None):
     """Statement-by-statement restatement of CGPtychoSolver.run (ptycho.py:283-488).
 
     Deviations, all deliberate and documented in DESIGN.md:
@@ -241,7 +266,7 @@ def cg_run(data, psi, scan, probe, piter, model="gaussian", recover_prb=False,
             p1 += np.abs(tmp1) ** 2
             p2 += np.abs(tmp2) ** 2
             p3 += 2 * (tmp1.real * tmp2.real + tmp1.imag * tmp2.imag)
-        gammapsi = 0.5 * line_search_sqr(minf, p1, p2, p3)
+        gammapsi = 0.5 * line_search_sqr(minf, p1, p2, p3, forced=forced_steps)
         psi = (psi + F32(gammapsi) * dpsi).astype(C64)
 
         if recover_prb:
@@ -277,7 +302,7 @@ def cg_run(data, psi, scan, probe, piter, model="gaussian", recover_prb=False,
                 tmp2 = _fwd(psi, dprb[:, m])
                 p2 = np.abs(tmp2) ** 2
                 p3 = 2 * (tmp1.real * tmp2.real + tmp1.imag * tmp2.imag)
-                gammaprb = 0.5 * line_search_sqr(minf, p1, p2, p3, step_length=1)
+                gammaprb = 0.5 * line_search_sqr(minf, p1, p2, p3, step_length=1, forced=forced_steps)
                 probe[:, m] = probe[:, m] + F32(gammaprb) * dprb[:, m]
         if history is not None:
             history.append((i, float(gammapsi), float(gammaprb), float(minf(absfpsi))))

@@ -143,18 +143,23 @@ class RefCGPtychoSolver(RefPtychoFFT):
 
     @staticmethod
     def line_search_sqr(f, p1, p2, p3, step_length=1, step_shrink=0.5, trials=None):
+        """ptycho.py:253-281; `trials` (diagnostics) collects (f(p1), [(step, f(step)), ...], result)."""
         assert step_shrink > 0 and step_shrink < 1
         m = 0
         fp1 = f(p1)
-        n = 1
-        while f(p1 + step_length ** 2 * p2 + step_length * p3) > fp1 + step_shrink * m:
+        seen = []
+        while True:
+            fs = f(p1 + step_length ** 2 * p2 + step_length * p3)
+            seen.append((step_length, float(fs)))
+            if not (fs > fp1 + step_shrink * m):
+                break
             if step_length < 1e-32:
                 warnings.warn("Line search failed for conjugate gradient.")
-                return 0
+                step_length = 0
+                break
             step_length *= step_shrink
-            n += 1
         if trials is not None:
-            trials.append(n)
+            trials.append((float(fp1), seen, step_length))
         return step_length
 
     def run(self, data, psi, scan, probe, piter, model="gaussian", recover_prb=False,

