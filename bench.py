@@ -59,7 +59,7 @@ def peaks():
 
 
 class ClockSampler(threading.Thread):
-    """SM clock / throttle reasons of one GPU while the timed region runs (NVML, 20 ms period)."""
+    """SM clock / throttle reasons of one GPU while the timed region runs (NVML, 5 ms period)."""
 
     def __init__(self, index):
         super().__init__(daemon=True)
@@ -93,7 +93,7 @@ class ClockSampler(threading.Thread):
                         self.reasons.add(name)
             except Exception:
                 break
-            time.sleep(0.02)
+            time.sleep(0.005)
 
     def stop(self):
         self._stop_evt.set()
