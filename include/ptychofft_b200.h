@@ -25,7 +25,7 @@
  *     SURVEY.md Q12).  Work is enqueued asynchronously; no host sync inside.
  *   - outputs of ptx_adj ACCUMULATE into caller-zeroed arrays, exactly like the
  *     reference's atomics (ptycho.py:102, 118); ptx_fwd overwrites g fully.
- *   - supported detector sizes in this build: ndet in {64, 128}; nprb <= ndet.
+ *   - supported detector sizes in this build: ndet in {64, 128, 256, 512}; nprb <= ndet.
  *     Anything else fails loudly with PTX_EUNSUPPORTED (there is no CPU or
  *     library fallback).
  */

@@ -184,20 +184,27 @@ struct NoBatch {
   static constexpr int bit(int) { return 0; }
 };
 
-// Shared-memory geometry of a tile: row stride N+4 complex and an XOR swizzle of the two low
-// column bits with column bits 5:4.  With 64-bit accesses (16 lanes per wavefront) every stage
-// of the plans below is bank-conflict free: bank pair = (4*y + x') mod 16.
-template <int L>
-struct TileGeom {
-  static constexpr int N = 1 << L;
-  static constexpr int RS = N + 4;
-  static constexpr int WORDS = N * RS;  // float2 elements
-  static PTX_HD int idx(int y, int x) { return y * RS + (x ^ ((x >> 4) & 3)); }
-};
-
 // ---------------------------------------------------------------- plans
+// Plan<L>, L = log2(detector size N).  A CTA of NT threads works on one LOCAL tile of NY x NX
+// complex values (always 16384 for N >= 128) with E = 32 registers per thread and three 2-D radix
+// stages S0..S2.  For N > 128 the N x N frame is RC = N^2/16384 local tiles: a "cross" radix-RC
+// butterfly along y (digit y[L-1 : L-LC], natural-order thread ownership of N x N/RC column blocks)
+// splits the frame into RC independent NY x NX sub-transforms (sub-tile k1 holds the rows of output
+// frequency ky = k1 mod RC), which are staged through an L2-resident scratch frame.
+//
+// Shared-memory geometry of a tile: row stride NX+4 complex and an XOR swizzle swz(x) of the low
+// column bits with higher column bits.  With 64-bit accesses (16 lanes per wavefront) every stage
+// of the plans below is bank-conflict free: bank pair = (4*y + (x ^ swz(x))) mod 16
+// (audited on the CPU by tests/emu_fft.cpp).
 template <int L>
 struct Plan;
+
+template <class P>
+struct TileGeom {
+  static constexpr int RS = P::NX + 4;
+  static constexpr int WORDS = P::NY * RS;  // float2 elements
+  static PTX_HD int idx(int y, int x) { return y * RS + (x ^ P::swz(x)); }
+};
 
 // N = 128: 512 threads x 32 elements; x = 3+2+2 bits, y = 2+3+2 bits (+1 batch bit on y).
 struct W128_1 {  // free bits: x[3:0], y[4:0]
@@ -221,10 +228,12 @@ struct W128_3 {  // free bits: x[6:2], y[6:3]; lanes = x4,x5,x2,x3,x6 (coalesced
 };
 template <>
 struct Plan<7> {
-  static constexpr int L = 7, N = 128, E = 32, NT = N * N / E, NSTAGE = 3, WBITS = 9;
+  static constexpr int L = 7, N = 128, LX = 7, LY = 7, NX = 128, NY = 128, RC = 1, LC = 0;
+  static constexpr int E = 32, NT = NX * NY / E, NSTAGE = 3, WBITS = 9;
   using S0 = Stage<4, 3, 5, 2, 0, NoBatch, W128_1>;
   using S1 = Stage<2, 2, 2, 3, 0, NoBatch, W128_2>;
   using S2 = Stage<0, 2, 0, 2, 1, B128_3, W128_3>;
+  static PTX_HD int swz(int x) { return (x >> 4) & 3; }
 };
 
 // N = 64: 128 threads x 32 elements; x = 3+3 bits, y = 2+2+2 (last stage: radix-4 on y, 8 batches).
@@ -248,10 +257,63 @@ struct W64_3 {  // active y[1:0]; free: x[5:2], y[5:3]; lanes x4,x5,x2,x3,y3
 };
 template <>
 struct Plan<6> {
-  static constexpr int L = 6, N = 64, E = 32, NT = N * N / E, NSTAGE = 3, WBITS = 7;
+  static constexpr int L = 6, N = 64, LX = 6, LY = 6, NX = 64, NY = 64, RC = 1, LC = 0;
+  static constexpr int E = 32, NT = NX * NY / E, NSTAGE = 3, WBITS = 7;
   using S0 = Stage<3, 3, 4, 2, 0, NoBatch, W64_1>;
   using S1 = Stage<0, 3, 2, 2, 0, NoBatch, W64_2>;
   using S2 = Stage<0, 0, 0, 2, 3, B64_3, W64_3>;
+  static PTX_HD int swz(int x) { return (x >> 4) & 3; }
+};
+
+// N = 256: cross radix 4 on y[7:6]; local tile 64 (y) x 256 (x): x = 3+3+2 bits, y = 2+2+2 bits.
+struct WBIG_0 {  // free bits: x[4:0], y[3:0]; lanes x0..x4 (coalesced scratch rows)
+  static constexpr int bit(int j) { return j < 5 ? j : (16 + (j - 5)); }
+};
+struct W256_1 {  // active x[4:2], y[3:2]; free: x[1:0], y[1:0], x[7:5], y[5:4]; lanes x0,x1,y0,y1,x5
+  static constexpr int bit(int j) {
+    return j < 2 ? j : j < 4 ? (16 + (j - 2)) : j < 7 ? (5 + (j - 4)) : (16 + 4 + (j - 7));
+  }
+};
+struct B256_2 {  // batch bit: y[5]
+  static constexpr int bit(int) { return 16 + 5; }
+};
+struct W256_2 {  // active x[1:0], y[1:0]; lanes x5,x6,x7,x2,x3 (= frequency bits 0..4), then x4, y[4:2]
+  static constexpr int bit(int j) {
+    return j < 3 ? (5 + j) : j < 6 ? (2 + (j - 3)) : (16 + 2 + (j - 6));
+  }
+};
+template <>
+struct Plan<8> {
+  static constexpr int L = 8, N = 256, LX = 8, LY = 6, NX = 256, NY = 64, RC = 4, LC = 2;
+  static constexpr int E = 32, NT = NX * NY / E, NSTAGE = 3, WBITS = 9;
+  using S0 = Stage<5, 3, 4, 2, 0, NoBatch, WBIG_0>;
+  using S1 = Stage<2, 3, 2, 2, 0, NoBatch, W256_1>;
+  using S2 = Stage<0, 2, 0, 2, 1, B256_2, W256_2>;
+  static PTX_HD int swz(int x) { return ((x >> 5) & 3) | (((x >> 7) & 1) << 3); }
+};
+
+// N = 512: cross radix 16 on y[8:5]; local tile 32 (y) x 512 (x): x = 4+3+2 bits, y = 1+2+2 bits.
+struct W512_1 {  // active x[4:2], y[3:2]; free: x[1:0], y[1:0], x[8:5], y[4]; lanes x0,x1,y0,y1,x5
+  static constexpr int bit(int j) {
+    return j < 2 ? j : j < 4 ? (16 + (j - 2)) : j < 8 ? (5 + (j - 4)) : (16 + 4);
+  }
+};
+struct B512_2 {  // batch bit: y[4]
+  static constexpr int bit(int) { return 16 + 4; }
+};
+struct W512_2 {  // active x[1:0], y[1:0]; lanes x5..x8,x2 (= frequency bits 0..4), then x3,x4,y2,y3
+  static constexpr int bit(int j) {
+    return j < 4 ? (5 + j) : j < 7 ? (2 + (j - 4)) : (16 + 2 + (j - 7));
+  }
+};
+template <>
+struct Plan<9> {
+  static constexpr int L = 9, N = 512, LX = 9, LY = 5, NX = 512, NY = 32, RC = 16, LC = 4;
+  static constexpr int E = 32, NT = NX * NY / E, NSTAGE = 3, WBITS = 9;
+  using S0 = Stage<5, 4, 4, 1, 0, NoBatch, WBIG_0>;
+  using S1 = Stage<2, 3, 2, 2, 0, NoBatch, W512_1>;
+  using S2 = Stage<0, 2, 0, 2, 1, B512_2, W512_2>;
+  static PTX_HD int swz(int x) { return (x >> 5) & 15; }
 };
 
 // ---------------------------------------------------------------- coordinates of a thread's elements
@@ -304,7 +366,8 @@ struct TwLayout {
   static constexpr int Y1 = X1 + TwSize<typename P::S1>::X;
   static constexpr int X2 = Y1 + TwSize<typename P::S1>::Y;
   static constexpr int Y2 = X2 + TwSize<typename P::S2>::X;
-  static constexpr int TOTAL = Y2 + TwSize<typename P::S2>::Y;
+  static constexpr int CROSS = Y2 + TwSize<typename P::S2>::Y;  // W_N^(ylow k1), [k1-1][ylow]
+  static constexpr int TOTAL = CROSS + (P::RC > 1 ? (P::RC - 1) * P::NY : 0);
 };
 
 // host-side fill (double precision -> float)
@@ -334,6 +397,14 @@ inline void fill_twiddles(float2* tw) {
   fill_twiddles_stage<typename P::S0>(tw + TL::X0, tw + TL::Y0);
   fill_twiddles_stage<typename P::S1>(tw + TL::X1, tw + TL::Y1);
   fill_twiddles_stage<typename P::S2>(tw + TL::X2, tw + TL::Y2);
+  if (P::RC > 1) {
+    const double PI2 = 6.283185307179586476925286766559;
+    for (int k = 1; k < P::RC; ++k)
+      for (int m = 0; m < P::NY; ++m) {
+        double a = -PI2 * (double)(m * k) / (double)P::N;
+        tw[TL::CROSS + (k - 1) * P::NY + m] = make_float2((float)cos(a), (float)sin(a));
+      }
+  }
 }
 
 // ---------------------------------------------------------------- one stage, in registers
@@ -398,22 +469,22 @@ PTX_HD void stage_compute(float2 (&v)[ST::E], int xf, int yf, const float2* twx,
   }
 }
 
-template <class ST, int L>
+template <class ST, class P>
 PTX_HD void stage_load(float2 (&v)[ST::E], const float2* tile, int xf, int yf) {
 #pragma unroll
   for (int e = 0; e < ST::E; ++e) {
     int dx, dy;
     elem_offset<ST>(e, dx, dy);
-    v[e] = tile[TileGeom<L>::idx(yf | dy, xf | dx)];
+    v[e] = tile[TileGeom<P>::idx(yf | dy, xf | dx)];
   }
 }
-template <class ST, int L>
+template <class ST, class P>
 PTX_HD void stage_store(const float2 (&v)[ST::E], float2* tile, int xf, int yf) {
 #pragma unroll
   for (int e = 0; e < ST::E; ++e) {
     int dx, dy;
     elem_offset<ST>(e, dx, dy);
-    tile[TileGeom<L>::idx(yf | dy, xf | dx)] = v[e];
+    tile[TileGeom<P>::idx(yf | dy, xf | dx)] = v[e];
   }
 }
 
@@ -439,6 +510,55 @@ PTX_HD int pos_to_freq_y(int p) {
   const int k2 = (p >> B::YLO) & (B::RY - 1);
   const int k3 = (p >> C::YLO) & (C::RY - 1);
   return k1 + A::RY * (k2 + B::RY * k3);
+}
+
+// ---------------------------------------------------------------- cross stage (N > 128)
+// Natural ("cross") ownership of column block c: thread tid owns, for b < E/RC, the RC elements
+// (y = j*NY + ylow, x = c*CW + xc), j < RC, with pair index p = tid + NT*b, xc = p % CW, ylow = p / CW
+// (CW = NX/RC = NY).  Register e = j + RC*b.  For RC = 1 the natural ownership is stage-0 ownership.
+template <class P>
+struct Cross {
+  static constexpr int RC = P::RC, CW = P::NX / P::RC, NB = P::E / P::RC;
+  static constexpr int LCW = P::LX - P::LC;  // log2(CW)
+  static PTX_HD void pair(int tid, int b, int& ylow, int& xc) {
+    const int p = tid + P::NT * b;
+    xc = p & (CW - 1);
+    ylow = p >> LCW;
+  }
+};
+
+// forward: radix-RC butterfly over j, then twiddle W_N^(ylow*k1); inverse: conjugates, reversed.
+template <class P, bool INV>
+PTX_HD void cross_compute(float2 (&v)[P::E], int tid, const float2* twc) {
+  using C = Cross<P>;
+  if (INV) {
+#pragma unroll
+    for (int b = 0; b < C::NB; ++b) {
+      int ylow, xc;
+      C::pair(tid, b, ylow, xc);
+#pragma unroll
+      for (int k = 1; k < P::RC; ++k)
+        v[k + P::RC * b] = cmulc(v[k + P::RC * b], twc[(k - 1) * P::NY + ylow]);
+    }
+  }
+#pragma unroll
+  for (int b = 0; b < C::NB; ++b) Dft<P::RC, INV, 1, P::E>::run(v, P::RC * b);
+  if (!INV) {
+#pragma unroll
+    for (int b = 0; b < C::NB; ++b) {
+      int ylow, xc;
+      C::pair(tid, b, ylow, xc);
+#pragma unroll
+      for (int k = 1; k < P::RC; ++k)
+        v[k + P::RC * b] = cmul(v[k + P::RC * b], twc[(k - 1) * P::NY + ylow]);
+    }
+  }
+}
+
+// scratch frame layout: sub-tile k1 is a contiguous NY x NX row-major block
+template <class P>
+PTX_HD int scratch_index(int k1, int ylow, int x) {
+  return (k1 * P::NY + ylow) * P::NX + x;
 }
 
 }  // namespace ptx

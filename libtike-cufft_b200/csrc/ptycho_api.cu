@@ -1,0 +1,492 @@
+// C ABI of the B200-native ptychography library (include/ptychofft_b200.h): plan object, launch
+// glue for the fused kernels of ptycho_passes.cuh, and the small vector kernels of the CG loop.
+//
+// Replaces /root/reference/src/cuda/{ptychofft.cu,kernels.cu} (cuFFT plan + muloperator) and the
+// CuPy elementwise/reduction code of src/libtike/cufft/ptycho.py:283-488.  Built in-tree by
+// __graft_entry__.build() with
+//   nvcc -gencode arch=compute_100a,code=sm_100a -lineinfo -O3 -shared -Xcompiler -fPIC
+// There is no CPU or library fallback: unsupported sizes return PTX_EUNSUPPORTED.
+#include <cuda_runtime.h>
+#include <stdarg.h>
+#include <stdio.h>
+#include <stdlib.h>
+#include <string.h>
+
+#include <atomic>
+#include <new>
+#include <vector>
+
+#include "../../include/ptychofft_b200.h"
+#include "ptycho_ops.h"
+
+namespace ptx {
+
+// ------------------------------------------------------------------------------------------
+// small vector kernels on object / probe sized arrays
+// ------------------------------------------------------------------------------------------
+__global__ void k_dy_reduce(const float2* __restrict__ gr, const float2* __restrict__ g0,
+                            const float2* __restrict__ d, size_t n, double* out) {
+  __shared__ double red[8 * 3];
+  double acc[3] = {0.0, 0.0, 0.0};
+  for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n;
+       i += (size_t)gridDim.x * blockDim.x) {
+    const float2 a = gr[i], b = g0[i], c = d[i];
+    const float2 df = make_float2(a.x - b.x, a.y - b.y);
+    acc[0] += (double)(a.x * a.x + a.y * a.y);
+    acc[1] += (double)(c.x * df.x + c.y * df.y);  // conj(d) * (g - g0)
+    acc[2] += (double)(c.x * df.y - c.y * df.x);
+  }
+  block_reduce_add<3, 8>(acc, red, out, threadIdx.x);
+}
+
+__global__ void k_dy_update(const float2* __restrict__ gr, float2* __restrict__ g0,
+                            float2* __restrict__ d, size_t n, const double* red, int first) {
+  float2 beta = make_float2(0.f, 0.f);
+  if (!first) {
+    // beta = ||g||^2 / (sum conj(d)(g-g0)) : a real divided by a complex (ptycho.py:369-371)
+    const double nr = red[0], re = red[1], im = red[2];
+    const double den = re * re + im * im;
+    beta = make_float2((float)(nr * re / den), (float)(-nr * im / den));
+  }
+  for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n;
+       i += (size_t)gridDim.x * blockDim.x) {
+    const float2 a = gr[i];
+    float2 r = make_float2(-a.x, -a.y);
+    if (!first) {
+      const float2 c = d[i];
+      r.x += beta.x * c.x - beta.y * c.y;
+      r.y += beta.x * c.y + beta.y * c.x;
+    }
+    d[i] = r;
+    g0[i] = a;
+  }
+}
+
+__global__ void k_axpy(float2* __restrict__ y, const float2* __restrict__ x, size_t n,
+                       const float* alpha) {
+  const float al = *alpha;
+  for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n;
+       i += (size_t)gridDim.x * blockDim.x) {
+    float2 a = y[i];
+    const float2 b = x[i];
+    a.x += al * b.x;
+    a.y += al * b.y;
+    y[i] = a;
+  }
+}
+
+__global__ void k_scale(float2* __restrict__ x, size_t n, const float* s) {
+  const float sc = *s;
+  for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n;
+       i += (size_t)gridDim.x * blockDim.x) {
+    float2 a = x[i];
+    a.x *= sc;
+    a.y *= sc;
+    x[i] = a;
+  }
+}
+
+__global__ void k_absmax(const float2* __restrict__ x, size_t n, float* out) {
+  float m = 0.f;
+  for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n;
+       i += (size_t)gridDim.x * blockDim.x) {
+    const float2 a = x[i];
+    m = fmaxf(m, a.x * a.x + a.y * a.y);
+  }
+#pragma unroll
+  for (int off = 16; off > 0; off >>= 1) m = fmaxf(m, __shfl_down_sync(0xffffffffu, m, off));
+  // non-negative floats order like their bit patterns
+  if ((threadIdx.x & 31) == 0) atomicMax(reinterpret_cast<int*>(out), __float_as_int(sqrtf(m)));
+}
+
+}  // namespace ptx
+
+// ==========================================================================================
+// host side: plan object and C ABI
+// ==========================================================================================
+using namespace ptx;
+
+static thread_local char g_err[512] = "";
+static std::atomic<unsigned long long> g_launches{0};
+
+static int fail(int code, const char* fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(g_err, sizeof(g_err), fmt, ap);
+  va_end(ap);
+  return code;
+}
+#define CUDA_TRY(x)                                                                       \
+  do {                                                                                    \
+    cudaError_t e_ = (x);                                                                 \
+    if (e_ != cudaSuccess) return fail(PTX_ECUDA, "%s: %s", #x, cudaGetErrorString(e_)); \
+  } while (0)
+
+struct ptx_plan {
+  size_t ptheta, nz, n, nscan, ndet, nprb;
+  const PlanOps* ops;
+  bool freed;
+  int device, num_sms, grid;
+  float2* tw;
+  float2* scratch;
+  size_t scratch_per_cta;  // float2
+  Geo geo;
+};
+
+static const PlanOps* ops_for(int L) {
+  switch (L) {
+    case 6: return ops_l6();
+    case 7: return ops_l7();
+    case 8: return ops_l8();
+    case 9: return ops_l9();
+  }
+  return nullptr;
+}
+
+static int plan_init(ptx_plan* p) {
+  const PlanOps* ops = p->ops;
+  std::vector<float2> tw(ops->tw_total + 1);
+  ops->fill_tw(tw.data());
+  CUDA_TRY(cudaMalloc(&p->tw, tw.size() * sizeof(float2)));
+  CUDA_TRY(cudaMemcpy(p->tw, tw.data(), tw.size() * sizeof(float2), cudaMemcpyHostToDevice));
+  // opt in to the large dynamic shared-memory carve-out for every kernel of this size class
+  for (int k = 0; k < K_COUNT; ++k)
+    CUDA_TRY(cudaFuncSetAttribute(ops->kernels[k], cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                  (int)ops->smem_bytes));
+  // persistent grid: as many CTAs as fit at once
+  int per_sm = 0;
+  CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, ops->kernels[K_GRAD_GAUSS_OBJ],
+                                                         ops->NT, ops->smem_bytes));
+  if (per_sm < 1)
+    return fail(PTX_ECUDA, "kernel does not fit on an SM (smem %zu B)", ops->smem_bytes);
+  p->grid = p->num_sms * per_sm;
+  const size_t npat = p->ptheta * p->nscan;
+  if ((size_t)p->grid > npat) p->grid = (int)npat;
+  // per-CTA scratch: [frame (N > 128) | stash / probe accumulators | p1,p2,p3 accumulators]
+  p->scratch_per_cta = ops->scratch_per_cta;
+  CUDA_TRY(cudaMalloc(&p->scratch, p->scratch_per_cta * p->grid * sizeof(float2)));
+  return PTX_OK;
+}
+
+static bool debug_sync() {
+  static const bool on = getenv("PTX_DEBUG_SYNC") != nullptr;
+  return on;
+}
+
+static int launch(ptx_plan* p, int kid, PassArgs& a, cudaStream_t st) {
+  const PlanOps* ops = p->ops;
+  const int npat = a.g.T * a.g.S;
+  const int grid = npat < p->grid ? npat : p->grid;
+  void* params[] = {&a};
+  cudaError_t e = cudaLaunchKernel(ops->kernels[kid], dim3(grid), dim3(ops->NT), params,
+                                   ops->smem_bytes, st);
+  g_launches.fetch_add(1);
+  if (e != cudaSuccess) return fail(PTX_ECUDA, "launch %s: %s", ops->names[kid], cudaGetErrorString(e));
+  CUDA_TRY(cudaGetLastError());
+  if (debug_sync()) {  // PTX_DEBUG_SYNC=1: attribute asynchronous faults to the kernel that raised them
+    e = cudaStreamSynchronize(st);
+    if (e != cudaSuccess)
+      return fail(PTX_ECUDA, "%s (grid %d): %s", ops->names[kid], grid, cudaGetErrorString(e));
+  }
+  return PTX_OK;
+}
+
+static int check_plan(const ptx_plan* p) {
+  if (!p) return fail(PTX_EINVAL, "null plan");
+  if (p->freed) return fail(PTX_EFREED, "plan used after free()");
+  return PTX_OK;
+}
+
+static PassArgs base_args(const ptx_plan* p) {
+  PassArgs a;
+  memset(&a, 0, sizeof(a));
+  a.g = p->geo;
+  a.tw = p->tw;
+  a.scratch = p->scratch;
+  a.scratch_per_cta = p->scratch_per_cta;
+  return a;
+}
+
+extern "C" {
+
+const char* ptx_last_error(void) { return g_err; }
+
+unsigned long long ptx_launch_count(void) { return g_launches.load(); }
+
+int ptx_device_ok(void) {
+  int n = 0;
+  if (cudaGetDeviceCount(&n) != cudaSuccess || n < 1) {
+    cudaGetLastError();
+    return 0;
+  }
+  int dev = 0, major = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess) return 0;
+  if (cudaDeviceGetAttribute(&major, cudaDevAttrComputeCapabilityMajor, dev) != cudaSuccess) return 0;
+  return major == 10 ? 1 : 0;
+}
+
+int ptx_create(ptx_plan** out, size_t ptheta, size_t nz, size_t n, size_t nscan, size_t ndet,
+               size_t nprb) {
+  if (!out) return fail(PTX_EINVAL, "null out pointer");
+  *out = nullptr;
+  if (!ptheta || !nz || !n || !nscan || !ndet || !nprb)
+    return fail(PTX_EINVAL, "all sizes must be positive");
+  if (nprb > ndet) return fail(PTX_EINVAL, "probe_shape %zu exceeds detector_shape %zu", nprb, ndet);
+  if (nprb + 1 > nz || nprb + 1 > n)
+    return fail(PTX_EINVAL, "object %zux%zu too small for a %zu probe", nz, n, nprb);
+  int L = 0;
+  while (((size_t)1 << L) < ndet) ++L;
+  if (((size_t)1 << L) != ndet || !ops_for(L))
+    return fail(PTX_EUNSUPPORTED,
+                "detector_shape=%zu: this build has sm_100a kernels for 64, 128, 256 and 512 only "
+                "(no CPU or cuFFT fallback)", ndet);
+  if (ptheta * nscan > 0x7fffffffull / 2) return fail(PTX_EINVAL, "too many patterns per call");
+  ptx_plan* p = new (std::nothrow) ptx_plan();
+  if (!p) return fail(PTX_EINVAL, "out of host memory");
+  p->ptheta = ptheta; p->nz = nz; p->n = n; p->nscan = nscan; p->ndet = ndet; p->nprb = nprb;
+  p->ops = ops_for(L);
+  p->freed = false;
+  p->tw = nullptr;
+  p->scratch = nullptr;
+  p->geo.T = (int)ptheta; p->geo.nz = (int)nz; p->geo.n = (int)n; p->geo.S = (int)nscan;
+  p->geo.P = (int)nprb; p->geo.N = (int)ndet; p->geo.o = (int)((ndet - nprb) / 2);
+  p->geo.kappa = 1.0f / (float)ndet;
+  cudaError_t e = cudaGetDevice(&p->device);
+  if (e == cudaSuccess) e = cudaDeviceGetAttribute(&p->num_sms, cudaDevAttrMultiProcessorCount, p->device);
+  int major = 0;
+  if (e == cudaSuccess) e = cudaDeviceGetAttribute(&major, cudaDevAttrComputeCapabilityMajor, p->device);
+  if (e != cudaSuccess) {
+    delete p;
+    return fail(PTX_ECUDA, "no usable CUDA device: %s", cudaGetErrorString(e));
+  }
+  if (major != 10) {
+    delete p;
+    return fail(PTX_EUNSUPPORTED, "device compute capability %d.x: this library is sm_100a only", major);
+  }
+  int rc = plan_init(p);
+  if (rc) {
+    if (p->tw) cudaFree(p->tw);
+    if (p->scratch) cudaFree(p->scratch);
+    delete p;
+    return rc;
+  }
+  *out = p;
+  return PTX_OK;
+}
+
+int ptx_free(ptx_plan* p) {
+  if (!p) return fail(PTX_EINVAL, "null plan");
+  if (!p->freed) {
+    cudaFree(p->tw);
+    cudaFree(p->scratch);
+    p->tw = nullptr;
+    p->scratch = nullptr;
+    p->freed = true;
+  }
+  return PTX_OK;
+}
+
+int ptx_destroy(ptx_plan* p) {
+  if (!p) return PTX_OK;
+  ptx_free(p);
+  delete p;
+  return PTX_OK;
+}
+
+size_t ptx_dim(const ptx_plan* p, int which) {
+  if (!p) return 0;
+  switch (which) {
+    case PTX_DIM_PTHETA: return p->ptheta;
+    case PTX_DIM_NZ: return p->nz;
+    case PTX_DIM_N: return p->n;
+    case PTX_DIM_NSCAN: return p->nscan;
+    case PTX_DIM_NDET: return p->ndet;
+    case PTX_DIM_NPRB: return p->nprb;
+  }
+  return 0;
+}
+
+int ptx_fwd(ptx_plan* p, void* g, const void* f, const void* scan, const void* prb,
+            size_t prb_angle_stride, void* stream) {
+  int rc = check_plan(p);
+  if (rc) return rc;
+  if (!g || !f || !scan || !prb) return fail(PTX_EINVAL, "ptx_fwd: null array");
+  PassArgs a = base_args(p);
+  a.far = (float2*)g;
+  a.psi = (const float2*)f;
+  a.scan = (const float2*)scan;
+  a.prb = (const float2*)prb;
+  a.prb_ts = prb_angle_stride ? prb_angle_stride : p->nprb * p->nprb;
+  return launch(p, K_FWD, a, (cudaStream_t)stream);
+}
+
+int ptx_debug_nearplane(ptx_plan* p, void* near, const void* f, const void* scan, const void* prb,
+                        size_t prb_angle_stride, void* stream) {
+  int rc = check_plan(p);
+  if (rc) return rc;
+  if (!near || !f || !scan || !prb) return fail(PTX_EINVAL, "ptx_debug_nearplane: null array");
+  PassArgs a = base_args(p);
+  a.far = (float2*)near;
+  a.psi = (const float2*)f;
+  a.scan = (const float2*)scan;
+  a.prb = (const float2*)prb;
+  a.prb_ts = prb_angle_stride ? prb_angle_stride : p->nprb * p->nprb;
+  return launch(p, K_NEAR, a, (cudaStream_t)stream);
+}
+
+int ptx_adj(ptx_plan* p, void* f, const void* g, const void* scan, void* prb,
+            size_t prb_angle_stride, int flg, void* stream) {
+  int rc = check_plan(p);
+  if (rc) return rc;
+  if (!g || !f || !scan || !prb) return fail(PTX_EINVAL, "ptx_adj: null array");
+  if (flg != 0 && flg != 1) return fail(PTX_EINVAL, "ptx_adj: flg must be 0 (object) or 1 (probe)");
+  PassArgs a = base_args(p);
+  a.far_in = (const float2*)g;
+  a.scan = (const float2*)scan;
+  const size_t ts = prb_angle_stride ? prb_angle_stride : p->nprb * p->nprb;
+  if (flg == 0) {
+    a.grad = (float2*)f;
+    a.prb = (const float2*)prb;
+    a.prb_ts = ts;
+    return launch(p, K_ADJ_OBJ, a, (cudaStream_t)stream);
+  } else {
+    a.psi = (const float2*)f;
+    a.grad = (float2*)prb;
+    a.grad_ts = ts;
+    return launch(p, K_ADJ_PRB, a, (cudaStream_t)stream);
+  }
+}
+
+int ptx_cg_intensity(ptx_plan* p, const void* psi, const void* scan, const void* probe, int nmodes,
+                     const float* data, float* inten_out, const float* iscale_dev, int model,
+                     double* red, void* stream) {
+  int rc = check_plan(p);
+  if (rc) return rc;
+  if (!psi || !scan || !probe || !data || !red || nmodes < 1)
+    return fail(PTX_EINVAL, "ptx_cg_intensity: bad argument");
+  PassArgs a = base_args(p);
+  a.psi = (const float2*)psi;
+  a.scan = (const float2*)scan;
+  a.prb = (const float2*)probe;
+  a.prb_ms = p->nprb * p->nprb;
+  a.prb_ts = a.prb_ms * nmodes;
+  a.nmodes = nmodes;
+  a.data = data;
+  a.inten_out = inten_out;
+  a.sc = iscale_dev;
+  a.red = red;
+  if (model == PTX_MODEL_GAUSSIAN) return launch(p, K_INT_GAUSS, a, (cudaStream_t)stream);
+  if (model == PTX_MODEL_POISSON) return launch(p, K_INT_POIS, a, (cudaStream_t)stream);
+  return fail(PTX_EINVAL, "unknown model %d", model);
+}
+
+int ptx_cg_grad(ptx_plan* p, int what, const void* psi, const void* scan, const void* probe,
+                int nmodes, int mode, const float* data, const float* inten_in, const float* sc,
+                int model, void* grad_out, size_t grad_angle_stride, void* stream) {
+  int rc = check_plan(p);
+  if (rc) return rc;
+  if (!psi || !scan || !probe || !data || !sc || !grad_out || nmodes < 1 || mode < 0 ||
+      mode >= nmodes || (what != 0 && what != 1))
+    return fail(PTX_EINVAL, "ptx_cg_grad: bad argument");
+  PassArgs a = base_args(p);
+  const size_t pp = p->nprb * p->nprb;
+  a.psi = (const float2*)psi;
+  a.scan = (const float2*)scan;
+  a.prb = (const float2*)probe + (size_t)mode * pp;
+  a.prb_ts = pp * nmodes;
+  a.data = data;
+  a.inten_in = inten_in;
+  a.sc = sc;
+  a.grad = (float2*)grad_out;
+  a.grad_ts = grad_angle_stride ? grad_angle_stride : pp;
+  cudaStream_t st = (cudaStream_t)stream;
+  if (model == PTX_MODEL_GAUSSIAN)
+    return launch(p, what == 0 ? K_GRAD_GAUSS_OBJ : K_GRAD_GAUSS_PRB, a, st);
+  if (model == PTX_MODEL_POISSON)
+    return launch(p, what == 0 ? K_GRAD_POIS_OBJ : K_GRAD_POIS_PRB, a, st);
+  return fail(PTX_EINVAL, "unknown model %d", model);
+}
+
+int ptx_cg_linesearch(ptx_plan* p, const void* obj_a, const void* prb_a, int nmodes_a, int mode_a0,
+                      const void* obj_b, const void* prb_b, int nmodes_b, int mode_b0, int npairs,
+                      const void* scan, const float* data, const float* p1_in, int model, int c0,
+                      int ncand, double* cost, void* stream) {
+  int rc = check_plan(p);
+  if (rc) return rc;
+  if (!obj_a || !prb_a || !obj_b || !prb_b || !scan || !data || !cost || npairs < 1 || ncand < 1 ||
+      ncand > 8 || c0 < 0 || mode_a0 < 0 || mode_b0 < 0 || mode_a0 + npairs > nmodes_a ||
+      mode_b0 + npairs > nmodes_b)
+    return fail(PTX_EINVAL, "ptx_cg_linesearch: bad argument");
+  PassArgs a = base_args(p);
+  const size_t pp = p->nprb * p->nprb;
+  a.psi = (const float2*)obj_a;
+  a.psi_b = (const float2*)obj_b;
+  a.prb = (const float2*)prb_a + (size_t)mode_a0 * pp;
+  a.prb_b = (const float2*)prb_b + (size_t)mode_b0 * pp;
+  a.prb_ts = pp * nmodes_a;
+  a.prb_b_ts = pp * nmodes_b;
+  a.prb_ms = pp;
+  a.prb_b_ms = pp;
+  a.scan = (const float2*)scan;
+  a.data = data;
+  a.inten_in = p1_in;
+  a.npairs = npairs;
+  a.c0 = c0;
+  a.ncand = ncand;
+  a.red = cost;
+  cudaStream_t st = (cudaStream_t)stream;
+  if (model == PTX_MODEL_GAUSSIAN) return launch(p, K_LS_GAUSS, a, st);
+  if (model == PTX_MODEL_POISSON) return launch(p, K_LS_POIS, a, st);
+  return fail(PTX_EINVAL, "unknown model %d", model);
+}
+
+static int vec_grid(size_t n) {
+  size_t b = (n + 255) / 256;
+  return (int)(b < 1 ? 1 : (b > 1184 ? 1184 : b));
+}
+
+int ptx_vec_dai_yuan_reduce(const void* g, const void* g0, const void* d, size_t n, double* red,
+                            void* stream) {
+  if (!g || !g0 || !d || !red) return fail(PTX_EINVAL, "ptx_vec_dai_yuan_reduce: null array");
+  k_dy_reduce<<<vec_grid(n), 256, 0, (cudaStream_t)stream>>>((const float2*)g, (const float2*)g0,
+                                                             (const float2*)d, n, red);
+  g_launches.fetch_add(1);
+  CUDA_TRY(cudaGetLastError());
+  return PTX_OK;
+}
+
+int ptx_vec_dai_yuan_update(const void* g, void* g0, void* d, size_t n, const double* red, int first,
+                            void* stream) {
+  if (!g || !g0 || !d || !red) return fail(PTX_EINVAL, "ptx_vec_dai_yuan_update: null array");
+  k_dy_update<<<vec_grid(n), 256, 0, (cudaStream_t)stream>>>((const float2*)g, (float2*)g0,
+                                                             (float2*)d, n, red, first);
+  g_launches.fetch_add(1);
+  CUDA_TRY(cudaGetLastError());
+  return PTX_OK;
+}
+
+int ptx_vec_axpy(void* y, const void* x, size_t n, const float* alpha_dev, void* stream) {
+  if (!y || !x || !alpha_dev) return fail(PTX_EINVAL, "ptx_vec_axpy: null array");
+  k_axpy<<<vec_grid(n), 256, 0, (cudaStream_t)stream>>>((float2*)y, (const float2*)x, n, alpha_dev);
+  g_launches.fetch_add(1);
+  CUDA_TRY(cudaGetLastError());
+  return PTX_OK;
+}
+
+int ptx_vec_scale(void* x, size_t n, const float* s_dev, void* stream) {
+  if (!x || !s_dev) return fail(PTX_EINVAL, "ptx_vec_scale: null array");
+  k_scale<<<vec_grid(n), 256, 0, (cudaStream_t)stream>>>((float2*)x, n, s_dev);
+  g_launches.fetch_add(1);
+  CUDA_TRY(cudaGetLastError());
+  return PTX_OK;
+}
+
+int ptx_vec_absmax(const void* x, size_t n, float* out, void* stream) {
+  if (!x || !out) return fail(PTX_EINVAL, "ptx_vec_absmax: null array");
+  k_absmax<<<vec_grid(n), 256, 0, (cudaStream_t)stream>>>((const float2*)x, n, out);
+  g_launches.fetch_add(1);
+  CUDA_TRY(cudaGetLastError());
+  return PTX_OK;
+}
+
+}  // extern "C"

@@ -1,11 +1,17 @@
 // Device building blocks of the fused ptychography kernels (sm_100a).
 //
 // One CTA owns one diffraction pattern at a time (persistent loop over patterns).  The pattern's
-// N x N complex tile is staged through shared memory by the register-resident FFT of
-// fft_tile.cuh; everything else -- patch gather with bilinear sub-pixel weights, probe multiply,
-// zero padding, residual against the measured data, conjugate-probe multiply, bilinear
-// scatter-add -- is done on the registers / the shared tile of the same CTA, so the far field
-// never visits HBM in the fused passes.
+// frame is staged through shared memory by the register-resident FFT of fft_tile.cuh; everything
+// else -- patch gather with bilinear sub-pixel weights, probe multiply, zero padding, residual
+// against the measured data, conjugate-probe multiply, bilinear scatter-add -- is done on the
+// registers / the shared tile of the same CTA, so the far field never visits HBM in the fused
+// passes.  Detectors larger than 128^2 do not fit one SM: their frame is cut into RC = N^2/16384
+// local tiles by a radix-RC "cross" butterfly and staged through a per-CTA scratch frame that
+// stays L2-resident (4 x 8 N^2 bytes of L2 traffic per pattern, no HBM round trip).
+//
+// "Natural ownership" of column block cb (cb < RC): which near-plane pixels (y, x) the 32 registers
+// of a thread hold before the forward / after the inverse transform -- stage-0 ownership of the
+// whole tile for RC = 1, the cross-stage ownership of fft_tile.cuh (N rows x N/RC columns) else.
 //
 // Reference semantics reproduced here (paths relative to /root/reference):
 //   scan split / skip rule / indices ... src/cuda/kernels.cu:19-63
@@ -28,6 +34,7 @@ struct Geo {
 // Per-pattern, block-uniform context.
 struct Pat {
   int R, C;                  // integer patch origin (row, col): trunc toward zero like modff
+  float rho, gam;            // fractional parts (row, col)
   float w00, w01, w10, w11;  // bilinear weights, kernels.cu:97-100
   bool skip;                 // integer part negative -> pattern skipped (kernels.cu:39)
   bool inside;               // the (P+1) x (P+1) window lies fully inside the object
@@ -36,15 +43,16 @@ struct Pat {
 __device__ __forceinline__ Pat make_pat(const float2* __restrict__ scan, int idx, const Geo& g) {
   const float2 sc = __ldg(scan + idx);  // .x = row (vertical), .y = column (horizontal)
   const float rI = truncf(sc.x), cI = truncf(sc.y);
-  const float rho = sc.x - rI, gam = sc.y - cI;
   Pat p;
+  p.rho = sc.x - rI;
+  p.gam = sc.y - cI;
   p.skip = (rI < 0.f) || (cI < 0.f);  // -0.0 is not < 0: (-1,0) is NOT skipped, as in the reference
   p.R = (int)rI;
   p.C = (int)cI;
-  p.w00 = (1.f - gam) * (1.f - rho);
-  p.w01 = gam * (1.f - rho);
-  p.w10 = (1.f - gam) * rho;
-  p.w11 = gam * rho;
+  p.w00 = (1.f - p.gam) * (1.f - p.rho);
+  p.w01 = p.gam * (1.f - p.rho);
+  p.w10 = (1.f - p.gam) * p.rho;
+  p.w11 = p.gam * p.rho;
   p.inside = (p.R + g.P + 1 <= g.nz) && (p.C + g.P + 1 <= g.n);
   return p;
 }
@@ -75,17 +83,53 @@ __device__ __forceinline__ float2 patch_at(const float2* __restrict__ psi_t, con
   return t;
 }
 
-// near[o+iy, o+ix] = kappa * prb[iy,ix] * patch[iy,ix], zero elsewhere; in stage-0 ownership.
+// ---------------------------------------------------------------- per-CTA context
 template <class P>
-__device__ __forceinline__ void gather_s0(float2 (&v)[P::E], const float2* __restrict__ psi_t,
-                                          const float2* __restrict__ prb, const Geo& g,
-                                          const Pat& p, int xf, int yf) {
-  using ST = typename P::S0;
+struct Cta {
+  float2* tile;        // shared: NY x (NX+4) complex
+  const float2* tw;    // shared twiddle tables
+  double* red;         // shared reduction slots
+  float2* frame;       // global scratch frame [RC][NY][NX] (RC > 1 only)
+  float2* stash;       // global thread-private scratch, N*N complex: [(k*E + e)*NT + tid]
+  float* accp;         // global thread-private scratch, 3*N*N floats
+  int tid, xf0, yf0, xf2, yf2;
+};
+
+// frame coordinates (y, x) of natural-ownership register e of column block cb
+template <class P>
+__device__ __forceinline__ void nat_coord(const Cta<P>& c, int cb, int e, int& y, int& x) {
+  if (P::RC == 1) {
+    int dx, dy;
+    elem_offset<typename P::S0>(e, dx, dy);
+    y = c.yf0 | dy;
+    x = c.xf0 | dx;
+  } else {
+    int ylow, xc;
+    Cross<P>::pair(c.tid, e / P::RC, ylow, xc);
+    y = (e % P::RC) * P::NY + ylow;
+    x = cb * Cross<P>::CW + xc;
+  }
+}
+
+// natural frequency index ky*N + kx of spectrum register e (stage-2 ownership) of sub-tile k1
+template <class P>
+__device__ __forceinline__ int spec_index(const Cta<P>& c, int k1, int e) {
+  int dx, dy;
+  elem_offset<typename P::S2>(e, dx, dy);
+  return (k1 + P::RC * pos_to_freq_y<P>(c.yf2 | dy)) * P::N + pos_to_freq_x<P>(c.xf2 | dx);
+}
+
+// near[o+iy, o+ix] = kappa * prb[iy,ix] * patch[iy,ix], zero elsewhere; natural ownership of block cb.
+template <class P>
+__device__ __forceinline__ void gather_nat(float2 (&v)[P::E], const Cta<P>& c, int cb,
+                                           const float2* __restrict__ psi_t,
+                                           const float2* __restrict__ prb, const Geo& g,
+                                           const Pat& p) {
 #pragma unroll
   for (int e = 0; e < P::E; ++e) {
-    int dx, dy;
-    elem_offset<ST>(e, dx, dy);
-    const int iy = (yf | dy) - g.o, ix = (xf | dx) - g.o;
+    int y, x;
+    nat_coord<P>(c, cb, e, y, x);
+    const int iy = y - g.o, ix = x - g.o;
     float2 r = make_float2(0.f, 0.f);
     if ((unsigned)iy < (unsigned)g.P && (unsigned)ix < (unsigned)g.P) {
       const float2 t = patch_at(psi_t, g, p, iy, ix);
@@ -97,25 +141,24 @@ __device__ __forceinline__ void gather_s0(float2 (&v)[P::E], const float2* __res
   }
 }
 
-// ---------------------------------------------------------------- CTA-wide transforms
+// ---------------------------------------------------------------- CTA-wide local transforms
 // forward: v (stage-0 ownership, natural order) -> v (stage-2 ownership, digit-reversed spectrum)
 template <class P>
 __device__ __forceinline__ void fft_forward(float2 (&v)[P::E], float2* tile, const float2* tw,
                                             int tid) {
   using TL = TwLayout<P>;
-  constexpr int L = P::L;
   int xf, yf;
   fixed_coords<typename P::S0, P::WBITS>(tid, xf, yf);
   stage_compute<typename P::S0, false>(v, xf, yf, tw + TL::X0, tw + TL::Y0);
-  stage_store<typename P::S0, L>(v, tile, xf, yf);
+  stage_store<typename P::S0, P>(v, tile, xf, yf);
   __syncthreads();
   fixed_coords<typename P::S1, P::WBITS>(tid, xf, yf);
-  stage_load<typename P::S1, L>(v, tile, xf, yf);
+  stage_load<typename P::S1, P>(v, tile, xf, yf);
   stage_compute<typename P::S1, false>(v, xf, yf, tw + TL::X1, tw + TL::Y1);
-  stage_store<typename P::S1, L>(v, tile, xf, yf);
+  stage_store<typename P::S1, P>(v, tile, xf, yf);
   __syncthreads();
   fixed_coords<typename P::S2, P::WBITS>(tid, xf, yf);
-  stage_load<typename P::S2, L>(v, tile, xf, yf);
+  stage_load<typename P::S2, P>(v, tile, xf, yf);
   stage_compute<typename P::S2, false>(v, xf, yf, tw + TL::X2, tw + TL::Y2);
 }
 
@@ -126,77 +169,275 @@ template <class P>
 __device__ __forceinline__ void fft_inverse(float2 (&v)[P::E], float2* tile, const float2* tw,
                                             int tid) {
   using TL = TwLayout<P>;
-  constexpr int L = P::L;
   int xf, yf;
   fixed_coords<typename P::S2, P::WBITS>(tid, xf, yf);
   stage_compute<typename P::S2, true>(v, xf, yf, tw + TL::X2, tw + TL::Y2);
-  stage_store<typename P::S2, L>(v, tile, xf, yf);
+  stage_store<typename P::S2, P>(v, tile, xf, yf);
   __syncthreads();
   fixed_coords<typename P::S1, P::WBITS>(tid, xf, yf);
-  stage_load<typename P::S1, L>(v, tile, xf, yf);
+  stage_load<typename P::S1, P>(v, tile, xf, yf);
   stage_compute<typename P::S1, true>(v, xf, yf, tw + TL::X1, tw + TL::Y1);
-  stage_store<typename P::S1, L>(v, tile, xf, yf);
+  stage_store<typename P::S1, P>(v, tile, xf, yf);
   __syncthreads();
   fixed_coords<typename P::S0, P::WBITS>(tid, xf, yf);
-  stage_load<typename P::S0, L>(v, tile, xf, yf);
+  stage_load<typename P::S0, P>(v, tile, xf, yf);
   stage_compute<typename P::S0, true>(v, xf, yf, tw + TL::X0, tw + TL::Y0);
 }
 
-// frequency (ky, kx) of spectrum register e of this thread (stage-2 ownership)
+// stage-0 ownership <-> scratch frame sub-tile k1 (L2-only accesses: written and read by
+// different threads of the same CTA with a block barrier in between)
 template <class P>
-__device__ __forceinline__ int spec_index(int e, int xf2, int yf2) {
-  int dx, dy;
-  elem_offset<typename P::S2>(e, dx, dy);
-  return pos_to_freq_y<P>(yf2 | dy) * P::N + pos_to_freq_x<P>(xf2 | dx);
-}
-
-// ---------------------------------------------------------------- object adjoint: scatter-add
-// v holds the near field in stage-0 ownership.  t = scale * conj(prb) * near is parked in the shared
-// tile, then every output pixel of the (P+1) x (P+1) window combines its four bilinear taps and
-// issues ONE vector reduction (red.global.add.v2.f32) instead of the reference's 8 scalar atomics
-// per input pixel (kernels.cu:73-80).
-template <class P>
-__device__ __forceinline__ void scatter_obj(float2 (&v)[P::E], float2* tile,
-                                            const float2* __restrict__ prb, float scale,
-                                            float2* __restrict__ grad_t, const Geo& g, const Pat& p,
-                                            int tid) {
-  using ST = typename P::S0;
-  using G = TileGeom<P::L>;
-  int xf, yf;
-  fixed_coords<ST, P::WBITS>(tid, xf, yf);
+__device__ __forceinline__ void frame_load_s0(float2 (&v)[P::E], const Cta<P>& c, int k1) {
+  const float2* f = c.frame + (size_t)k1 * P::NX * P::NY;
 #pragma unroll
   for (int e = 0; e < P::E; ++e) {
     int dx, dy;
-    elem_offset<ST>(e, dx, dy);
-    const int y = yf | dy, x = xf | dx;
-    const int iy = y - g.o, ix = x - g.o;
-    if ((unsigned)iy < (unsigned)g.P && (unsigned)ix < (unsigned)g.P) {
-      const float2 pr = __ldg(prb + iy * g.P + ix);
-      float2 t;  // conj(prb) * near
-      t.x = scale * (pr.x * v[e].x + pr.y * v[e].y);
-      t.y = scale * (pr.x * v[e].y - pr.y * v[e].x);
-      tile[G::idx(y, x)] = t;
+    elem_offset<typename P::S0>(e, dx, dy);
+    v[e] = __ldcg(f + (c.yf0 | dy) * P::NX + (c.xf0 | dx));
+  }
+}
+template <class P>
+__device__ __forceinline__ void frame_store_s0(const float2 (&v)[P::E], const Cta<P>& c, int k1) {
+  float2* f = c.frame + (size_t)k1 * P::NX * P::NY;
+#pragma unroll
+  for (int e = 0; e < P::E; ++e) {
+    int dx, dy;
+    elem_offset<typename P::S0>(e, dx, dy);
+    __stcg(f + (c.yf0 | dy) * P::NX + (c.xf0 | dx), v[e]);
+  }
+}
+// cross (natural) ownership of block cb <-> scratch frame: register j + RC*b <-> sub-tile j
+template <class P>
+__device__ __forceinline__ void frame_load_cross(float2 (&v)[P::E], const Cta<P>& c, int cb) {
+#pragma unroll
+  for (int e = 0; e < P::E; ++e) {
+    int ylow, xc;
+    Cross<P>::pair(c.tid, e / P::RC, ylow, xc);
+    v[e] = __ldcg(c.frame + scratch_index<P>(e % P::RC, ylow, cb * Cross<P>::CW + xc));
+  }
+}
+template <class P>
+__device__ __forceinline__ void frame_store_cross(const float2 (&v)[P::E], const Cta<P>& c, int cb) {
+#pragma unroll
+  for (int e = 0; e < P::E; ++e) {
+    int ylow, xc;
+    Cross<P>::pair(c.tid, e / P::RC, ylow, xc);
+    __stcg(c.frame + scratch_index<P>(e % P::RC, ylow, cb * Cross<P>::CW + xc), v[e]);
+  }
+}
+
+// ---------------------------------------------------------------- pattern-level passes
+// gather(cb, v): fill v with the near plane of column block cb in natural ownership.
+// point(k1, v):  consume / modify the spectrum of sub-tile k1 (stage-2 ownership, spec_index).
+// near(cb, v):   consume the near plane of column block cb after the inverse transform.
+// Every pass ends with the shared tile free for reuse (trailing block barrier).
+
+// forward only: fwd operator, intensities, line-search costs.  `zero`: the pattern is skipped,
+// its far field is identically 0 and point() is evaluated on zeros without any transform.
+template <class P, class Gather, class Point>
+__device__ __forceinline__ void spectrum_pass(const Cta<P>& c, bool zero, Gather gather, Point point) {
+  float2 v[P::E];
+  if (zero) {
+    for (int k1 = 0; k1 < P::RC; ++k1) {
+#pragma unroll
+      for (int e = 0; e < P::E; ++e) v[e] = make_float2(0.f, 0.f);
+      point(k1, v);
+    }
+    return;
+  }
+  if (P::RC == 1) {
+    gather(0, v);
+    fft_forward<P>(v, c.tile, c.tw, c.tid);
+    point(0, v);
+    __syncthreads();
+  } else {
+    for (int cb = 0; cb < P::RC; ++cb) {
+      gather(cb, v);
+      cross_compute<P, false>(v, c.tid, c.tw + TwLayout<P>::CROSS);
+      frame_store_cross<P>(v, c, cb);
+    }
+    __syncthreads();
+    for (int k1 = 0; k1 < P::RC; ++k1) {
+      frame_load_s0<P>(v, c, k1);
+      fft_forward<P>(v, c.tile, c.tw, c.tid);
+      point(k1, v);
+      __syncthreads();
     }
   }
+}
+
+// forward -> pointwise -> inverse with the spectrum kept in registers (the fused gradient)
+template <class P, class Gather, class Point, class Near>
+__device__ __forceinline__ void fused_pass(const Cta<P>& c, Gather gather, Point point, Near near) {
+  float2 v[P::E];
+  if (P::RC == 1) {
+    gather(0, v);
+    fft_forward<P>(v, c.tile, c.tw, c.tid);
+    point(0, v);
+    fft_inverse<P>(v, c.tile, c.tw, c.tid);
+    near(0, v);
+  } else {
+    for (int cb = 0; cb < P::RC; ++cb) {
+      gather(cb, v);
+      cross_compute<P, false>(v, c.tid, c.tw + TwLayout<P>::CROSS);
+      frame_store_cross<P>(v, c, cb);
+    }
+    __syncthreads();
+    for (int k1 = 0; k1 < P::RC; ++k1) {
+      frame_load_s0<P>(v, c, k1);
+      fft_forward<P>(v, c.tile, c.tw, c.tid);
+      point(k1, v);
+      fft_inverse<P>(v, c.tile, c.tw, c.tid);
+      frame_store_s0<P>(v, c, k1);  // the positions this thread loaded: no hazard
+      __syncthreads();              // tile reuse by the next sub-tile; frame complete after the last
+    }
+    for (int cb = 0; cb < P::RC; ++cb) {
+      frame_load_cross<P>(v, c, cb);
+      cross_compute<P, true>(v, c.tid, c.tw + TwLayout<P>::CROSS);
+      near(cb, v);
+    }
+    __syncthreads();  // frame reuse by the next pattern
+  }
+}
+
+// inverse only: the API adjoints.  load(k1, v) fills the spectrum registers of sub-tile k1.
+template <class P, class Load, class Near>
+__device__ __forceinline__ void inverse_pass(const Cta<P>& c, Load load, Near near) {
+  float2 v[P::E];
+  if (P::RC == 1) {
+    load(0, v);
+    fft_inverse<P>(v, c.tile, c.tw, c.tid);
+    near(0, v);
+    __syncthreads();  // the next inverse starts by writing stage-2 positions other threads just read
+  } else {
+    for (int k1 = 0; k1 < P::RC; ++k1) {
+      load(k1, v);
+      fft_inverse<P>(v, c.tile, c.tw, c.tid);
+      frame_store_s0<P>(v, c, k1);
+      __syncthreads();
+    }
+    for (int cb = 0; cb < P::RC; ++cb) {
+      frame_load_cross<P>(v, c, cb);
+      cross_compute<P, true>(v, c.tid, c.tw + TwLayout<P>::CROSS);
+      near(cb, v);
+    }
+    __syncthreads();
+  }
+}
+
+// ---------------------------------------------------------------- object adjoint: scatter-add
+// v holds the near plane of column block cb (natural ownership).  t = scale * conj(prb) * near is
+// parked in the shared tile as an N-row x CW-column block; then every thread walks one column of
+// the block over a run of 32 rows, forms the bilinear spread separably
+//     h[y][x] = (1-gam) t[y][x] + gam t[y][x-1],   out[y][x] = (1-rho) h[y][x] + rho h[y-1][x]
+// in registers (2 shared loads per output pixel) and issues ONE vector reduction
+// (red.global.add.v2.f32) per object pixel instead of the reference's 8 scalar atomics per probe
+// pixel (kernels.cu:73-80).  The column to the right of the block only receives the gam * t part
+// (the neighbouring block adds its own share: the adds commute).  Leaves the tile free (trailing barrier).
+template <class P>
+__device__ __forceinline__ void scatter_block(float2 (&v)[P::E], const Cta<P>& c, int cb,
+                                              const float2* __restrict__ prb, float scale,
+                                              float2* __restrict__ grad_t, const Geo& g,
+                                              const Pat& p) {
+  constexpr int ROWS = P::N, COLS = Cross<P>::CW;
+  constexpr int PITCH = TileGeom<P>::WORDS / ROWS;
+  constexpr int RUN = ROWS * COLS / P::NT;  // 32 output rows per thread
+  static_assert(PITCH >= COLS, "scatter block must fit the tile");
+  float2* tile = c.tile;
+  __syncthreads();  // other threads may still be reading the tile (last inverse stage)
+#pragma unroll
+  for (int e = 0; e < P::E; ++e) {
+    int y, x;
+    nat_coord<P>(c, cb, e, y, x);
+    const int iy = y - g.o, ix = x - g.o;
+    float2 t = make_float2(0.f, 0.f);
+    if ((unsigned)iy < (unsigned)g.P && (unsigned)ix < (unsigned)g.P) {
+      const float2 pr = __ldg(prb + iy * g.P + ix);
+      t.x = scale * (pr.x * v[e].x + pr.y * v[e].y);  // conj(prb) * near
+      t.y = scale * (pr.x * v[e].y - pr.y * v[e].x);
+    }
+    tile[y * PITCH + (x - cb * COLS)] = t;
+  }
   __syncthreads();
-  const int lane = tid & 31, warp = tid >> 5;
-  constexpr int NW = P::NT / 32;
-  const int W = g.P + 1;
-  const float2 z = make_float2(0.f, 0.f);
-  for (int i = warp; i < W; i += NW) {
-    const int r = p.R + i;
-    if (r >= g.nz) break;
-    for (int j = lane; j < W; j += 32) {
-      const int c = p.C + j;
-      const bool up = i > 0, lo = i < g.P, lf = j > 0, rt = j < g.P;
-      const float2 a = (lo && rt) ? tile[G::idx(g.o + i, g.o + j)] : z;
-      const float2 b = (lo && lf) ? tile[G::idx(g.o + i, g.o + j - 1)] : z;
-      const float2 cc = (up && rt) ? tile[G::idx(g.o + i - 1, g.o + j)] : z;
-      const float2 d = (up && lf) ? tile[G::idx(g.o + i - 1, g.o + j - 1)] : z;
-      float2 out;
-      out.x = a.x * p.w00 + b.x * p.w01 + cc.x * p.w10 + d.x * p.w11;
-      out.y = a.y * p.w00 + b.y * p.w01 + cc.y * p.w10 + d.y * p.w11;
-      if (c < g.n) atomicAdd(grad_t + (size_t)r * g.n + c, out);
+  const int xl = c.tid % COLS, r0 = (c.tid / COLS) * RUN;
+  const int x = cb * COLS + xl;                   // frame column of this thread's outputs
+  const int oc = p.C + x - g.o;                   // object column
+  const bool colok = (x >= g.o) && (x <= g.o + g.P) && (oc < g.n);
+  // the extra column right of the block: x + 1, fed by gam * t[.][xl] only
+  const bool extra = (xl == COLS - 1);
+  const bool ecolok = extra && (x + 1 >= g.o) && (x + 1 <= g.o + g.P) && (oc + 1 < g.n);
+  const float a0 = 1.f - p.gam, a1 = p.gam, b0 = 1.f - p.rho, b1 = p.rho;
+  float2 hp = make_float2(0.f, 0.f), ep = make_float2(0.f, 0.f);
+  if (r0 > 0) {
+    const float2 tc = tile[(r0 - 1) * PITCH + xl];
+    const float2 tl = xl > 0 ? tile[(r0 - 1) * PITCH + xl - 1] : make_float2(0.f, 0.f);
+    hp = make_float2(a0 * tc.x + a1 * tl.x, a0 * tc.y + a1 * tl.y);
+    ep = make_float2(a1 * tc.x, a1 * tc.y);
+  }
+  const int rlast = (r0 + RUN == ROWS) ? RUN + 1 : RUN;  // the last run also emits row ROWS
+#pragma unroll 4
+  for (int i = 0; i < rlast; ++i) {
+    const int y = r0 + i;
+    float2 hc = make_float2(0.f, 0.f), ec = make_float2(0.f, 0.f);
+    if (y < ROWS) {
+      const float2 tc = tile[y * PITCH + xl];
+      const float2 tl = xl > 0 ? tile[y * PITCH + xl - 1] : make_float2(0.f, 0.f);
+      hc = make_float2(a0 * tc.x + a1 * tl.x, a0 * tc.y + a1 * tl.y);
+      ec = make_float2(a1 * tc.x, a1 * tc.y);
+    }
+    const int orow = p.R + y - g.o;
+    const bool rowok = (y >= g.o) && (y <= g.o + g.P) && (orow < g.nz);
+    if (rowok) {
+      float2* dst = grad_t + (size_t)orow * g.n + oc;
+      if (colok) atomicAdd(dst, make_float2(b0 * hc.x + b1 * hp.x, b0 * hc.y + b1 * hp.y));
+      if (ecolok) atomicAdd(dst + 1, make_float2(b0 * ec.x + b1 * ep.x, b0 * ec.y + b1 * ep.y));
+    }
+    hp = hc;
+    ep = ec;
+  }
+  __syncthreads();
+}
+
+// ---------------------------------------------------------------- probe adjoint
+// thread-private accumulators in L2-resident scratch: acc[(cb*E + e)*NT + tid], natural ownership.
+// acc += scale * near * conj(patch)                                    (kernels.cu:82-94)
+template <class P>
+__device__ __forceinline__ void pacc_add(float2 (&v)[P::E], const Cta<P>& c, int cb,
+                                         const float2* __restrict__ psi_t, float scale,
+                                         const Geo& g, const Pat& p) {
+  float2* acc = c.stash + (size_t)cb * P::E * P::NT + c.tid;
+#pragma unroll
+  for (int e = 0; e < P::E; ++e) {
+    int y, x;
+    nat_coord<P>(c, cb, e, y, x);
+    const int iy = y - g.o, ix = x - g.o;
+    if ((unsigned)iy < (unsigned)g.P && (unsigned)ix < (unsigned)g.P) {
+      const float2 f = patch_at(psi_t, g, p, iy, ix);
+      float2 s = acc[e * P::NT];
+      s.x += scale * (v[e].x * f.x + v[e].y * f.y);
+      s.y += scale * (v[e].y * f.x - v[e].x * f.y);
+      acc[e * P::NT] = s;
+    }
+  }
+}
+template <class P>
+__device__ __forceinline__ void pacc_zero(const Cta<P>& c) {
+  for (int i = 0; i < P::RC * P::E; ++i) c.stash[(size_t)i * P::NT + c.tid] = make_float2(0.f, 0.f);
+}
+// one vector atomic per probe pixel per CTA and angle (reference: 2 scalar atomics per pattern)
+template <class P>
+__device__ __forceinline__ void pacc_flush(const Cta<P>& c, float2* __restrict__ gp, const Geo& g) {
+  for (int cb = 0; cb < P::RC; ++cb) {
+    float2* acc = c.stash + (size_t)cb * P::E * P::NT + c.tid;
+#pragma unroll
+    for (int e = 0; e < P::E; ++e) {
+      int y, x;
+      nat_coord<P>(c, cb, e, y, x);
+      const int iy = y - g.o, ix = x - g.o;
+      if ((unsigned)iy < (unsigned)g.P && (unsigned)ix < (unsigned)g.P) {
+        atomicAdd(gp + iy * g.P + ix, acc[e * P::NT]);
+        acc[e * P::NT] = make_float2(0.f, 0.f);
+      }
     }
   }
 }

@@ -1,0 +1,58 @@
+// Host-side glue between the C ABI (ptycho_api.cu) and the per-detector-size kernel families
+// (plan_l6.cu ... plan_l9.cu, one translation unit each so that they compile in parallel).
+#pragma once
+
+#include <cuda_runtime.h>
+#include <stddef.h>
+
+#include "ptycho_device.cuh"
+
+namespace ptx {
+
+// kernel parameter block, shared by every pass
+struct PassArgs {
+  Geo g;
+  const float2* tw;        // twiddle tables (global, copied to smem by every CTA)
+  float2* scratch;         // per-CTA scratch (L2 resident): [frame | stash | accp]
+  size_t scratch_per_cta;  // in float2
+  const float2* psi;       // [T,nz,n]
+  const float2* psi_b;     // second object (line search)
+  const float2* prb;       // probe base of the mode to use, angle stride prb_ts
+  const float2* prb_b;
+  size_t prb_ts, prb_b_ts;  // complex elements between angles
+  size_t prb_ms, prb_b_ms;  // complex elements between modes (pair loop)
+  const float2* scan;       // [T,S]
+  const float* data;        // [T,S,N,N]
+  const float* inten_in;    // [T,S,N,N] or null
+  float* inten_out;         // [T,S,N,N] or null
+  float2* far;              // [T,S,N,N]
+  const float2* far_in;
+  float2* grad;  // object gradient [T,nz,n] or probe gradient base (angle stride grad_ts)
+  size_t grad_ts;
+  const float* sc;  // device scalars
+  double* red;
+  int nmodes, npairs, c0, ncand;
+};
+
+enum KernelId {
+  K_FWD = 0, K_NEAR, K_ADJ_OBJ, K_ADJ_PRB, K_INT_GAUSS, K_INT_POIS,
+  K_GRAD_GAUSS_OBJ, K_GRAD_GAUSS_PRB, K_GRAD_POIS_OBJ, K_GRAD_POIS_PRB, K_LS_GAUSS, K_LS_POIS,
+  K_COUNT
+};
+
+struct PlanOps {
+  int L, N, NT, RC;
+  size_t smem_bytes;       // dynamic shared memory of every kernel of the family
+  size_t scratch_per_cta;  // float2
+  int tw_total;            // float2
+  void (*fill_tw)(float2*);
+  const void* kernels[K_COUNT];
+  const char* names[K_COUNT];
+};
+
+const PlanOps* ops_l6();
+const PlanOps* ops_l7();
+const PlanOps* ops_l8();
+const PlanOps* ops_l9();
+
+}  // namespace ptx

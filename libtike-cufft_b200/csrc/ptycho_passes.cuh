@@ -1,0 +1,402 @@
+// The fused sm_100a kernels, templated on the detector-size plan (fft_tile.cuh).
+//
+// Replaces /root/reference/src/cuda/{ptychofft.cu,kernels.cu} (cuFFT plan + muloperator) and the
+// CuPy elementwise/reduction code of src/libtike/cufft/ptycho.py:283-488.  Instantiated once per
+// detector size by plan_l6.cu .. plan_l9.cu; launched by ptycho_api.cu through PlanOps.
+#pragma once
+
+#include "../../include/ptychofft_b200.h"
+#include "ptycho_ops.h"
+
+namespace ptx {
+
+template <class P>
+struct Smem {
+  static constexpr int TILE = TileGeom<P>::WORDS;  // float2
+  static constexpr int TW = TwLayout<P>::TOTAL;    // float2
+  static constexpr int RED = (P::NT / 32) * 12;    // doubles
+  static constexpr size_t BYTES = (size_t)(TILE + TW) * sizeof(float2) + RED * sizeof(double);
+};
+
+template <class P>
+struct Scratch {  // per-CTA global scratch, in float2
+  static constexpr size_t FRAME = P::RC > 1 ? (size_t)P::N * P::N : 0;
+  static constexpr size_t STASH = (size_t)P::N * P::N;
+  static constexpr size_t ACCP = (size_t)3 * P::N * P::N / 2;
+  static constexpr size_t TOTAL = FRAME + STASH + ACCP;
+};
+
+template <class P>
+__device__ __forceinline__ void cta_setup(Cta<P>& c, unsigned char* raw, const PassArgs& a) {
+  c.tid = threadIdx.x;
+  c.tile = reinterpret_cast<float2*>(raw);
+  float2* tw = c.tile + Smem<P>::TILE;
+  c.red = reinterpret_cast<double*>(tw + Smem<P>::TW);
+  for (int i = c.tid; i < Smem<P>::TW; i += P::NT) tw[i] = a.tw[i];
+  c.tw = tw;
+  float2* scr = a.scratch + (size_t)blockIdx.x * a.scratch_per_cta;
+  c.frame = scr;
+  c.stash = scr + Scratch<P>::FRAME;
+  c.accp = reinterpret_cast<float*>(c.stash + Scratch<P>::STASH);
+  fixed_coords<typename P::S0, P::WBITS>(c.tid, c.xf0, c.yf0);
+  fixed_coords<typename P::S2, P::WBITS>(c.tid, c.xf2, c.yf2);
+  __syncthreads();
+}
+
+// Square root / division without the IEEE slow-path subroutine calls: MUFU.RSQ / MUFU.RCP plus one
+// Newton step, accurate to ~1 ulp for the non-negative, normal-range inputs of this path.
+__device__ __forceinline__ float fsqrt(float x) {
+  if (x < 1e-35f) return 0.f;
+  const float r = rsqrtf(x);
+  float s = x * r;                        // ~sqrt(x)
+  s = fmaf(fmaf(-s, s, x), 0.5f * r, s);  // one Newton step
+  return s;
+}
+__device__ __forceinline__ float fdiv(float a, float b) {
+  const float r = __frcp_rn(b);
+  const float q = a * r;
+  return fmaf(fmaf(-q, b, a), r, q);
+}
+
+// minimisation functional per pixel (ptycho.py:308-314), x = intensity estimate, d = data
+template <int MODEL>
+__device__ __forceinline__ float minf_px(float x, float d, float sqd) {
+  if (MODEL == PTX_MODEL_GAUSSIAN) {
+    const float r = fsqrt(fabsf(x)) - sqd;
+    return r * r;
+  } else {
+    const float ax = fabsf(x);
+    return ax - d * logf(ax + 1e-32f);
+  }
+}
+
+// ------------------------------------------------------------------------------------------
+// API forward: g = FFT2(pad(kappa * prb * patch))                      (ptychofft.cu:60-73)
+// ------------------------------------------------------------------------------------------
+template <class P>
+__global__ void __launch_bounds__(P::NT) k_fwd(const PassArgs a) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  Cta<P> c;
+  cta_setup<P>(c, smem_raw, a);
+  const Geo g = a.g;
+  const int npat = g.T * g.S;
+  for (int pat = blockIdx.x; pat < npat; pat += gridDim.x) {
+    const int t = pat / g.S;
+    const Pat p = make_pat(a.scan, pat, g);
+    float2* out = a.far + (size_t)pat * P::N * P::N;
+    const float2* psi_t = a.psi + (size_t)t * g.nz * g.n;
+    const float2* prb_t = a.prb + (size_t)t * a.prb_ts;
+    spectrum_pass<P>(
+        c, p.skip, [&](int cb, float2(&v)[P::E]) { gather_nat<P>(v, c, cb, psi_t, prb_t, g, p); },
+        [&](int k1, float2(&v)[P::E]) {
+#pragma unroll
+          for (int e = 0; e < P::E; ++e) out[spec_index<P>(c, k1, e)] = v[e];
+        });
+  }
+}
+
+// Parity hook: the zero-padded near-plane frame (kernels.cu:95-107 output, before the FFT), natural
+// order.  Integer work of the path (patch origin, window offset, skip rule) is checked bit-exactly
+// through it.
+template <class P>
+__global__ void __launch_bounds__(P::NT) k_nearplane(const PassArgs a) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  Cta<P> c;
+  cta_setup<P>(c, smem_raw, a);
+  const Geo g = a.g;
+  const int npat = g.T * g.S;
+  for (int pat = blockIdx.x; pat < npat; pat += gridDim.x) {
+    const int t = pat / g.S;
+    const Pat p = make_pat(a.scan, pat, g);
+    float2* out = a.far + (size_t)pat * P::N * P::N;
+    for (int cb = 0; cb < P::RC; ++cb) {
+      float2 v[P::E];
+      if (!p.skip) {
+        gather_nat<P>(v, c, cb, a.psi + (size_t)t * g.nz * g.n, a.prb + (size_t)t * a.prb_ts, g, p);
+      } else {
+#pragma unroll
+        for (int e = 0; e < P::E; ++e) v[e] = make_float2(0.f, 0.f);
+      }
+#pragma unroll
+      for (int e = 0; e < P::E; ++e) {
+        int y, x;
+        nat_coord<P>(c, cb, e, y, x);
+        out[y * P::N + x] = v[e];
+      }
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------
+// API adjoints: inverse FFT + object scatter (FLG 0) or probe reduction (FLG 1)  (ptychofft.cu:76-88)
+// ------------------------------------------------------------------------------------------
+template <class P, int FLG>
+__global__ void __launch_bounds__(P::NT) k_adj(const PassArgs a) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  Cta<P> c;
+  cta_setup<P>(c, smem_raw, a);
+  const Geo g = a.g;
+  if (FLG == 1) pacc_zero<P>(c);
+  int t_cur = -1;
+  const int npat = g.T * g.S;
+  for (int pat = blockIdx.x; pat < npat; pat += gridDim.x) {
+    const int t = pat / g.S;
+    if (FLG == 1 && t != t_cur) {
+      if (t_cur >= 0) pacc_flush<P>(c, a.grad + (size_t)t_cur * a.grad_ts, g);
+      t_cur = t;
+    }
+    const Pat p = make_pat(a.scan, pat, g);
+    if (p.skip) continue;
+    const float2* in = a.far_in + (size_t)pat * P::N * P::N;
+    const float2* psi_t = a.psi + (size_t)t * g.nz * g.n;
+    const float2* prb_t = a.prb + (size_t)t * a.prb_ts;
+    float2* grad_t = a.grad + (size_t)t * g.nz * g.n;
+    inverse_pass<P>(
+        c,
+        [&](int k1, float2(&v)[P::E]) {
+#pragma unroll
+          for (int e = 0; e < P::E; ++e) v[e] = __ldg(in + spec_index<P>(c, k1, e));
+        },
+        [&](int cb, float2(&v)[P::E]) {
+          if (FLG == 0)
+            scatter_block<P>(v, c, cb, prb_t, g.kappa, grad_t, g, p);
+          else
+            pacc_add<P>(v, c, cb, psi_t, g.kappa, g, p);
+        });
+  }
+  if (FLG == 1 && t_cur >= 0) pacc_flush<P>(c, a.grad + (size_t)t_cur * a.grad_ts, g);
+}
+
+// ------------------------------------------------------------------------------------------
+// CG pass A: I = sum_k |F_k|^2, reductions a = sum sqrt(I d), b = sum I, cost   (ptycho.py:330-343)
+// With several modes the running sum is parked in thread-private scratch between modes.
+// ------------------------------------------------------------------------------------------
+template <class P, int MODEL>
+__global__ void __launch_bounds__(P::NT) k_intensity(const PassArgs a) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  Cta<P> c;
+  cta_setup<P>(c, smem_raw, a);
+  const Geo g = a.g;
+  const float iscale = a.sc ? a.sc[0] : 1.f;
+  double acc[3] = {0.0, 0.0, 0.0};
+  const int npat = g.T * g.S;
+  for (int pat = blockIdx.x; pat < npat; pat += gridDim.x) {
+    const int t = pat / g.S;
+    const Pat p = make_pat(a.scan, pat, g);
+    const float2* psi_t = a.psi + (size_t)t * g.nz * g.n;
+    const float* d = a.data + (size_t)pat * P::N * P::N;
+    float* io = a.inten_out ? a.inten_out + (size_t)pat * P::N * P::N : nullptr;
+    float sa = 0.f, sb = 0.f, scost = 0.f;
+    const int kfirst = p.skip ? a.nmodes - 1 : 0;  // a skipped pattern has I = 0: one zero pass
+    for (int k = kfirst; k < a.nmodes; ++k) {
+      const float2* prb_k = a.prb + (size_t)t * a.prb_ts + (size_t)k * a.prb_ms;
+      const bool first = (k == kfirst), last = (k + 1 == a.nmodes);
+      spectrum_pass<P>(
+          c, p.skip, [&](int cb, float2(&v)[P::E]) { gather_nat<P>(v, c, cb, psi_t, prb_k, g, p); },
+          [&](int k1, float2(&v)[P::E]) {
+            float* ia = c.accp + (size_t)k1 * P::E * P::NT + c.tid;
+#pragma unroll
+            for (int e = 0; e < P::E; ++e) {
+              float I = v[e].x * v[e].x + v[e].y * v[e].y;
+              if (!first) I += ia[e * P::NT];
+              if (!last) {
+                ia[e * P::NT] = I;
+              } else {
+                const int idx = spec_index<P>(c, k1, e);
+                const float dd = __ldg(d + idx);
+                sa += fsqrt(I * dd);
+                sb += I;
+                scost += minf_px<MODEL>(I * iscale, dd, fsqrt(dd));
+                if (io) io[idx] = I;
+              }
+            }
+          });
+    }
+    acc[0] += (double)sa;
+    acc[1] += (double)sb;
+    acc[2] += (double)scost;
+  }
+  block_reduce_add<3, P::NT / 32>(acc, c.red, a.red, c.tid);
+}
+
+// ------------------------------------------------------------------------------------------
+// CG pass B/D: fused fwd -> residual -> inverse -> object scatter (WHAT 0) / probe reduction (WHAT 1)
+//   ptycho.py:347-363 (object), 421-441 (probe)
+// sc = {fscale, iscale, gscale}
+// ------------------------------------------------------------------------------------------
+template <class P, int MODEL, int WHAT>
+__global__ void __launch_bounds__(P::NT) k_grad(const PassArgs a) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  Cta<P> c;
+  cta_setup<P>(c, smem_raw, a);
+  const Geo g = a.g;
+  const float fscale = a.sc[0], iscale = a.sc[1], gscale = a.sc[2] * g.kappa;
+  if (WHAT == 1) pacc_zero<P>(c);
+  int t_cur = -1;
+  const int npat = g.T * g.S;
+  for (int pat = blockIdx.x; pat < npat; pat += gridDim.x) {
+    const int t = pat / g.S;
+    if (WHAT == 1 && t != t_cur) {
+      if (t_cur >= 0) pacc_flush<P>(c, a.grad + (size_t)t_cur * a.grad_ts, g);
+      t_cur = t;
+    }
+    const Pat p = make_pat(a.scan, pat, g);
+    if (p.skip) continue;  // F = 0 -> residual 0 -> no contribution
+    const float2* psi_t = a.psi + (size_t)t * g.nz * g.n;
+    const float2* prb_t = a.prb + (size_t)t * a.prb_ts;
+    float2* grad_t = a.grad + (size_t)t * g.nz * g.n;
+    const float* d = a.data + (size_t)pat * P::N * P::N;
+    const float* ii = a.inten_in ? a.inten_in + (size_t)pat * P::N * P::N : nullptr;
+    fused_pass<P>(
+        c, [&](int cb, float2(&v)[P::E]) { gather_nat<P>(v, c, cb, psi_t, prb_t, g, p); },
+        [&](int k1, float2(&v)[P::E]) {
+#pragma unroll
+          for (int e = 0; e < P::E; ++e) {
+            const int idx = spec_index<P>(c, k1, e);
+            const float dd = __ldg(d + idx);
+            const float I = ii ? __ldg(ii + idx) * iscale : (v[e].x * v[e].x + v[e].y * v[e].y);
+            float f;
+            if (MODEL == PTX_MODEL_GAUSSIAN)
+              f = fscale * (1.f - fdiv(fsqrt(dd), fsqrt(I) + 1e-32f));
+            else
+              f = fscale * (1.f - fdiv(dd, I + 1e-32f));
+            v[e].x *= f;
+            v[e].y *= f;
+          }
+        },
+        [&](int cb, float2(&v)[P::E]) {
+          if (WHAT == 0)
+            scatter_block<P>(v, c, cb, prb_t, gscale, grad_t, g, p);
+          else
+            pacc_add<P>(v, c, cb, psi_t, gscale, g, p);
+        });
+  }
+  if (WHAT == 1 && t_cur >= 0) pacc_flush<P>(c, a.grad + (size_t)t_cur * a.grad_ts, g);
+}
+
+// ------------------------------------------------------------------------------------------
+// CG pass C/E: line-search costs for up to 8 step candidates at once
+//   ptycho.py:383-393 (object), 451-461 (probe), 253-281 (line_search_sqr)
+// The first far field of a pair is parked in thread-private scratch while the second is transformed.
+// ------------------------------------------------------------------------------------------
+template <class P, int MODEL>
+__global__ void __launch_bounds__(P::NT) k_linesearch(const PassArgs a) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  Cta<P> c;
+  cta_setup<P>(c, smem_raw, a);
+  const Geo g = a.g;
+  constexpr size_t NN = (size_t)P::N * P::N;
+  double acc[9];
+#pragma unroll
+  for (int q = 0; q < 9; ++q) acc[q] = 0.0;
+  const bool multi = a.npairs > 1;
+  const int npat = g.T * g.S;
+  for (int pat = blockIdx.x; pat < npat; pat += gridDim.x) {
+    const int t = pat / g.S;
+    const Pat p = make_pat(a.scan, pat, g);
+    const float* d = a.data + (size_t)pat * NN;
+    const float* p1in = a.inten_in ? a.inten_in + (size_t)pat * NN : nullptr;
+    const float2* psi_a = a.psi + (size_t)t * g.nz * g.n;
+    const float2* psi_b = a.psi_b + (size_t)t * g.nz * g.n;
+    float cost[9];
+#pragma unroll
+    for (int q = 0; q < 9; ++q) cost[q] = 0.f;
+    for (int j = 0; j < a.npairs; ++j) {
+      const float2* prb_a = a.prb + (size_t)t * a.prb_ts + (size_t)j * a.prb_ms;
+      const float2* prb_b = a.prb_b + (size_t)t * a.prb_b_ts + (size_t)j * a.prb_b_ms;
+      const bool first = (j == 0), last = (j + 1 == a.npairs);
+      spectrum_pass<P>(
+          c, p.skip, [&](int cb, float2(&v)[P::E]) { gather_nat<P>(v, c, cb, psi_a, prb_a, g, p); },
+          [&](int k1, float2(&v)[P::E]) {
+            float2* st = c.stash + (size_t)k1 * P::E * P::NT + c.tid;
+#pragma unroll
+            for (int e = 0; e < P::E; ++e) st[e * P::NT] = v[e];
+          });
+      spectrum_pass<P>(
+          c, p.skip, [&](int cb, float2(&v)[P::E]) { gather_nat<P>(v, c, cb, psi_b, prb_b, g, p); },
+          [&](int k1, float2(&v)[P::E]) {
+            const float2* st = c.stash + (size_t)k1 * P::E * P::NT + c.tid;
+            float* ap = c.accp + (size_t)k1 * P::E * P::NT + c.tid;
+#pragma unroll
+            for (int e = 0; e < P::E; ++e) {
+              const float2 t1 = st[e * P::NT];
+              const float2 t2 = v[e];
+              float q1 = t1.x * t1.x + t1.y * t1.y;
+              float q2 = t2.x * t2.x + t2.y * t2.y;
+              float q3 = 2.f * (t1.x * t2.x + t1.y * t2.y);
+              if (multi) {
+                if (!first) {
+                  q1 += ap[e * P::NT];
+                  q2 += ap[NN + e * P::NT];
+                  q3 += ap[2 * NN + e * P::NT];
+                }
+                if (!last) {
+                  ap[e * P::NT] = q1;
+                  ap[NN + e * P::NT] = q2;
+                  ap[2 * NN + e * P::NT] = q3;
+                }
+              }
+              if (last) {
+                const int idx = spec_index<P>(c, k1, e);
+                const float dd = __ldg(d + idx);
+                const float sqd = fsqrt(dd);
+                if (p1in) q1 = __ldg(p1in + idx);
+                cost[0] += minf_px<MODEL>(q1, dd, sqd);
+                float gam = exp2f(-(float)a.c0);
+                for (int q = 0; q < a.ncand; ++q) {
+                  cost[1 + q] += minf_px<MODEL>(q1 + gam * gam * q2 + gam * q3, dd, sqd);
+                  gam *= 0.5f;
+                }
+              }
+            }
+          });
+    }
+#pragma unroll
+    for (int q = 0; q < 9; ++q) acc[q] += (double)cost[q];
+  }
+  block_reduce_add<9, P::NT / 32>(acc, c.red, a.red, c.tid);
+}
+
+// ------------------------------------------------------------------------------------------
+// the family's dispatch table
+// ------------------------------------------------------------------------------------------
+template <class P>
+static void fill_tw_host(float2* tw) {
+  fill_twiddles<P>(tw);
+}
+
+template <class P>
+const PlanOps* make_ops() {
+  static PlanOps ops;
+  static bool init = false;
+  if (!init) {
+    ops.L = P::L;
+    ops.N = P::N;
+    ops.NT = P::NT;
+    ops.RC = P::RC;
+    ops.smem_bytes = Smem<P>::BYTES;
+    ops.scratch_per_cta = Scratch<P>::TOTAL;
+    ops.tw_total = TwLayout<P>::TOTAL;
+    ops.fill_tw = fill_tw_host<P>;
+#define PTX_SET(id, ...)                                   \
+  ops.kernels[id] = (const void*)(void (*)(const PassArgs))(__VA_ARGS__); \
+  ops.names[id] = #__VA_ARGS__;
+    PTX_SET(K_FWD, k_fwd<P>)
+    PTX_SET(K_NEAR, k_nearplane<P>)
+    PTX_SET(K_ADJ_OBJ, k_adj<P, 0>)
+    PTX_SET(K_ADJ_PRB, k_adj<P, 1>)
+    PTX_SET(K_INT_GAUSS, k_intensity<P, 0>)
+    PTX_SET(K_INT_POIS, k_intensity<P, 1>)
+    PTX_SET(K_GRAD_GAUSS_OBJ, k_grad<P, 0, 0>)
+    PTX_SET(K_GRAD_GAUSS_PRB, k_grad<P, 0, 1>)
+    PTX_SET(K_GRAD_POIS_OBJ, k_grad<P, 1, 0>)
+    PTX_SET(K_GRAD_POIS_PRB, k_grad<P, 1, 1>)
+    PTX_SET(K_LS_GAUSS, k_linesearch<P, 0>)
+    PTX_SET(K_LS_POIS, k_linesearch<P, 1>)
+#undef PTX_SET
+    init = true;
+  }
+  return &ops;
+}
+
+}  // namespace ptx

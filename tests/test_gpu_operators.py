@@ -66,7 +66,9 @@ def test_c1_adjoint_identity():
 
 @pytest.mark.skipif(not ref_gpu.available(), reason="oracle/_ref not built")
 @pytest.mark.parametrize("cfg", [(128, 128, 276, 600, 64), (128, 96, 276, 600, 16),
-                                 (64, 64, 200, 220, 40), (64, 40, 200, 220, 9)])
+                                 (64, 64, 200, 220, 40), (64, 40, 200, 220, 9),
+                                 (256, 256, 300, 420, 12), (256, 200, 300, 420, 5),
+                                 (512, 512, 700, 640, 4), (512, 384, 700, 640, 3)])
 def test_operators_vs_compiled_reference(cfg):
     """Same inputs through the reference's own CUDA/cuFFT code on the same GPU."""
     pt = _pt()
@@ -107,7 +109,8 @@ def test_operators_vs_golden(name):
         assert rel_l2(slv.adj_ptycho_batch_prb(z["fwd"], scan, psi), z["adj_probe"]) < TOL
 
 
-@pytest.mark.parametrize("ndet,nprb", [(128, 128), (128, 100), (64, 64), (64, 30)])
+@pytest.mark.parametrize("ndet,nprb", [(128, 128), (128, 100), (64, 64), (64, 30), (256, 256),
+                                       (256, 130), (512, 512), (512, 78)])
 def test_integer_work_bit_exact(ndet, nprb):
     """Patch origin, window offset (ndet-nprb)/2 and the skip rule, bit for bit.
 
@@ -116,7 +119,7 @@ def test_integer_work_bit_exact(ndet, nprb):
     """
     from libtike.cufft.ptychofft import lib, check, current_stream
     pt = _pt()
-    nz, n, nscan = 150, 170, 12
+    nz, n, nscan = max(150, nprb + 22), max(170, nprb + 42), 12
     rng = np.random.default_rng(3)
     psi = (rng.integers(-512, 512, (1, nz, n)) + 1j * rng.integers(-512, 512, (1, nz, n))).astype(np.complex64)
     prb = np.ones((1, nprb, nprb), dtype=np.complex64)
@@ -176,6 +179,24 @@ def test_edge_positions_zero_extension():
         f = slv.adj_ptycho_batch(g0, scan, prb)
         f0 = O.adj(g0, scan, prb, nz + 2, n + 2)[:, :nz, :n]
         assert rel_l2(f, f0) < TOL
+
+
+@pytest.mark.parametrize("ndet", [256, 512])
+def test_large_detector_operators_vs_oracle(ndet):
+    """256^2 / 512^2 detectors (C4, C5): frame split into 4 / 16 tiles by the cross stage."""
+    pt = _pt()
+    nscan = 6 if ndet == 256 else 3
+    w = workloads.synth_angles(1, ndet + 60, ndet + 90, ndet, ndet, 2, 1, seed0=4)
+    psi, prb = w["psi"], w["probe"][:, 0]
+    rng = np.random.default_rng(ndet)
+    scan = np.stack([rng.uniform(0, 58.5, (1, nscan)), rng.uniform(0, 88.5, (1, nscan))],
+                    axis=-1).astype(np.float32)
+    scan[0, 1] = (58.25, 88.75)  # largest valid origin, fractional
+    with pt.PtychoCuFFT(nscan, ndet, ndet, 1, ndet + 60, ndet + 90) as slv:
+        g0 = O.fwd(psi, scan, prb, ndet)
+        assert rel_l2(slv.fwd_ptycho_batch(psi, scan, prb), g0) < TOL
+        assert rel_l2(slv.adj_ptycho_batch(g0, scan, prb), O.adj(g0, scan, prb, ndet + 60, ndet + 90)) < TOL
+        assert rel_l2(slv.adj_ptycho_batch_prb(g0, scan, psi), O.adj_probe(g0, scan, psi, ndet)) < TOL
 
 
 def test_raw_pointer_class_surface():
