@@ -192,18 +192,20 @@ struct NoBatch {
 // splits the frame into RC independent NY x NX sub-transforms (sub-tile k1 holds the rows of output
 // frequency ky = k1 mod RC), which are staged through an L2-resident scratch frame.
 //
-// Shared-memory geometry of a tile: row stride NX+4 complex and an XOR swizzle swz(x) of the low
-// column bits with higher column bits.  With 64-bit accesses (16 lanes per wavefront) every stage
-// of the plans below is bank-conflict free: bank pair = (4*y + (x ^ swz(x))) mod 16
-// (audited on the CPU by tests/emu_fft.cpp).
+// Shared-memory geometry of a tile: element (y, x) lives at y*RS + x + skew(x), where skew(x) is a
+// carry-free function of the HIGH column bits (bit-linear: skew(a|b) = skew(a) + skew(b) for
+// disjoint a, b) and RS = 4 mod 16.  With 64-bit accesses (16 lanes per wavefront) every stage of the
+// plans below is bank-conflict free: bank pair = (4*y + x + skew(x)) mod 16 (audited on the CPU by
+// tests/emu_fft.cpp).  Because both terms are additive in disjoint bit fields, a thread's 32
+// element addresses are ONE per-thread base plus compile-time immediates: no per-access index math.
 template <int L>
 struct Plan;
 
 template <class P>
 struct TileGeom {
-  static constexpr int RS = P::NX + 4;
+  static constexpr int RS = P::RS;
   static constexpr int WORDS = P::NY * RS;  // float2 elements
-  static PTX_HD int idx(int y, int x) { return y * RS + (x ^ P::swz(x)); }
+  static PTX_HD int idx(int y, int x) { return y * RS + x + P::skew(x); }
 };
 
 // N = 128: 512 threads x 32 elements; x = 3+2+2 bits, y = 2+3+2 bits (+1 batch bit on y).
@@ -233,7 +235,8 @@ struct Plan<7> {
   using S0 = Stage<4, 3, 5, 2, 0, NoBatch, W128_1>;
   using S1 = Stage<2, 2, 2, 3, 0, NoBatch, W128_2>;
   using S2 = Stage<0, 2, 0, 2, 1, B128_3, W128_3>;
-  static PTX_HD int swz(int x) { return (x >> 4) & 3; }
+  static constexpr int RS = 148;  // 128 + max skew 7, = 4 mod 16
+  static PTX_HD constexpr int skew(int x) { return x >> 4; }  // stage-2 lanes x4,x5 -> +1,+2
 };
 
 // N = 64: 128 threads x 32 elements; x = 3+3 bits, y = 2+2+2 (last stage: radix-4 on y, 8 batches).
@@ -262,7 +265,8 @@ struct Plan<6> {
   using S0 = Stage<3, 3, 4, 2, 0, NoBatch, W64_1>;
   using S1 = Stage<0, 3, 2, 2, 0, NoBatch, W64_2>;
   using S2 = Stage<0, 0, 0, 2, 3, B64_3, W64_3>;
-  static PTX_HD int swz(int x) { return (x >> 4) & 3; }
+  static constexpr int RS = 68;
+  static PTX_HD constexpr int skew(int x) { return (x >> 4) & 3; }
 };
 
 // N = 256: cross radix 4 on y[7:6]; local tile 64 (y) x 256 (x): x = 3+3+2 bits, y = 2+2+2 bits.
@@ -289,7 +293,10 @@ struct Plan<8> {
   using S0 = Stage<5, 3, 4, 2, 0, NoBatch, WBIG_0>;
   using S1 = Stage<2, 3, 2, 2, 0, NoBatch, W256_1>;
   using S2 = Stage<0, 2, 0, 2, 1, B256_2, W256_2>;
-  static PTX_HD int swz(int x) { return ((x >> 5) & 3) | (((x >> 7) & 1) << 3); }
+  static constexpr int RS = 276;  // 256 + max skew 11, = 4 mod 16
+  static PTX_HD constexpr int skew(int x) {  // stage-2 lanes x5,x6,x7 -> +1,+2,+8 (x2 gives +4)
+    return ((x >> 5) & 3) + (((x >> 7) & 1) << 3);
+  }
 };
 
 // N = 512: cross radix 16 on y[8:5]; local tile 32 (y) x 512 (x): x = 4+3+2 bits, y = 1+2+2 bits.
@@ -313,7 +320,8 @@ struct Plan<9> {
   using S0 = Stage<5, 4, 4, 1, 0, NoBatch, WBIG_0>;
   using S1 = Stage<2, 3, 2, 2, 0, NoBatch, W512_1>;
   using S2 = Stage<0, 2, 0, 2, 1, B512_2, W512_2>;
-  static PTX_HD int swz(int x) { return (x >> 5) & 15; }
+  static constexpr int RS = 532;  // 512 + max skew 15, = 4 mod 16
+  static PTX_HD constexpr int skew(int x) { return (x >> 5) & 15; }  // stage-2 lanes x5..x8
 };
 
 // ---------------------------------------------------------------- coordinates of a thread's elements
@@ -469,22 +477,26 @@ PTX_HD void stage_compute(float2 (&v)[ST::E], int xf, int yf, const float2* twx,
   }
 }
 
+// idx() is additive over the disjoint thread / element bit fields: one base per thread and stage,
+// compile-time immediates per element.
 template <class ST, class P>
 PTX_HD void stage_load(float2 (&v)[ST::E], const float2* tile, int xf, int yf) {
+  const float2* base = tile + TileGeom<P>::idx(yf, xf);
 #pragma unroll
   for (int e = 0; e < ST::E; ++e) {
     int dx, dy;
     elem_offset<ST>(e, dx, dy);
-    v[e] = tile[TileGeom<P>::idx(yf | dy, xf | dx)];
+    v[e] = base[TileGeom<P>::idx(dy, dx)];
   }
 }
 template <class ST, class P>
 PTX_HD void stage_store(const float2 (&v)[ST::E], float2* tile, int xf, int yf) {
+  float2* base = tile + TileGeom<P>::idx(yf, xf);
 #pragma unroll
   for (int e = 0; e < ST::E; ++e) {
     int dx, dy;
     elem_offset<ST>(e, dx, dy);
-    tile[TileGeom<P>::idx(yf | dy, xf | dx)] = v[e];
+    base[TileGeom<P>::idx(dy, dx)] = v[e];
   }
 }
 

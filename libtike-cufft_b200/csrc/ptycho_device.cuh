@@ -59,12 +59,13 @@ __device__ __forceinline__ Pat make_pat(const float2* __restrict__ scan, int idx
 
 // Bilinear object patch value at probe pixel (iy, ix).  Outside the object the field is taken as 0
 // (the reference reads out of bounds there).
+template <bool INSIDE>
 __device__ __forceinline__ float2 patch_at(const float2* __restrict__ psi_t, const Geo& g,
                                            const Pat& p, int iy, int ix) {
   const int r = p.R + iy, c = p.C + ix;
   const float2* q = psi_t + (size_t)r * g.n + c;
   float2 f00, f01, f10, f11;
-  if (p.inside) {
+  if (INSIDE) {
     f00 = __ldg(q);
     f01 = __ldg(q + 1);
     f10 = __ldg(q + g.n);
@@ -93,6 +94,7 @@ struct Cta {
   float2* stash;       // global thread-private scratch, N*N complex: [(k*E + e)*NT + tid]
   float* accp;         // global thread-private scratch, 3*N*N floats
   int tid, xf0, yf0, xf2, yf2;
+  int sbase;           // spec_index of the thread's stage-2 coordinates (element part is immediate)
 };
 
 // frame coordinates (y, x) of natural-ownership register e of column block cb
@@ -112,40 +114,62 @@ __device__ __forceinline__ void nat_coord(const Cta<P>& c, int cb, int e, int& y
 }
 
 // natural frequency index ky*N + kx of spectrum register e (stage-2 ownership) of sub-tile k1
+// (pos_to_freq is a bit permutation, hence additive over the disjoint thread / element bit fields)
+template <class P>
+__device__ __forceinline__ int spec_base(int xf2, int yf2) {
+  return P::RC * pos_to_freq_y<P>(yf2) * P::N + pos_to_freq_x<P>(xf2);
+}
 template <class P>
 __device__ __forceinline__ int spec_index(const Cta<P>& c, int k1, int e) {
   int dx, dy;
   elem_offset<typename P::S2>(e, dx, dy);
-  return (k1 + P::RC * pos_to_freq_y<P>(c.yf2 | dy)) * P::N + pos_to_freq_x<P>(c.xf2 | dx);
+  return c.sbase + k1 * P::N + (P::RC * pos_to_freq_y<P>(dy) * P::N + pos_to_freq_x<P>(dx));
 }
 
 // near[o+iy, o+ix] = kappa * prb[iy,ix] * patch[iy,ix], zero elsewhere; natural ownership of block cb.
-template <class P>
-__device__ __forceinline__ void gather_nat(float2 (&v)[P::E], const Cta<P>& c, int cb,
-                                           const float2* __restrict__ psi_t,
-                                           const float2* __restrict__ prb, const Geo& g,
-                                           const Pat& p) {
+// FULL: probe window == frame (P == N, o == 0), no window test; INSIDE: no object-bounds tests.
+template <class P, bool FULL, bool INSIDE>
+__device__ __forceinline__ void gather_impl(float2 (&v)[P::E], const Cta<P>& c, int cb,
+                                            const float2* __restrict__ psi_t,
+                                            const float2* __restrict__ prb, const Geo& g,
+                                            const Pat& p) {
 #pragma unroll
   for (int e = 0; e < P::E; ++e) {
     int y, x;
     nat_coord<P>(c, cb, e, y, x);
-    const int iy = y - g.o, ix = x - g.o;
+    const int iy = FULL ? y : y - g.o, ix = FULL ? x : x - g.o;
     float2 r = make_float2(0.f, 0.f);
-    if ((unsigned)iy < (unsigned)g.P && (unsigned)ix < (unsigned)g.P) {
-      const float2 t = patch_at(psi_t, g, p, iy, ix);
+    if (FULL || ((unsigned)iy < (unsigned)g.P && (unsigned)ix < (unsigned)g.P)) {
       const float2 pr = __ldg(prb + iy * g.P + ix);
+      const float2 t = patch_at<INSIDE>(psi_t, g, p, iy, ix);
       r.x = g.kappa * (pr.x * t.x - pr.y * t.y);
       r.y = g.kappa * (pr.x * t.y + pr.y * t.x);
     }
     v[e] = r;
   }
 }
+template <class P>
+__device__ __forceinline__ void gather_nat(float2 (&v)[P::E], const Cta<P>& c, int cb,
+                                           const float2* __restrict__ psi_t,
+                                           const float2* __restrict__ prb, const Geo& g,
+                                           const Pat& p) {
+  if (g.P == P::N) {  // block-uniform
+    if (p.inside)
+      gather_impl<P, true, true>(v, c, cb, psi_t, prb, g, p);
+    else
+      gather_impl<P, true, false>(v, c, cb, psi_t, prb, g, p);
+  } else {
+    gather_impl<P, false, false>(v, c, cb, psi_t, prb, g, p);
+  }
+}
 
 // ---------------------------------------------------------------- CTA-wide local transforms
 // forward: v (stage-0 ownership, natural order) -> v (stage-2 ownership, digit-reversed spectrum)
-template <class P>
+// `pre()` runs between the second exchange and the last stage: the place to issue the global loads
+// (measured data) that the pointwise step needs, so that their latency hides behind stage 2.
+template <class P, class Pre>
 __device__ __forceinline__ void fft_forward(float2 (&v)[P::E], float2* tile, const float2* tw,
-                                            int tid) {
+                                            int tid, Pre pre) {
   using TL = TwLayout<P>;
   int xf, yf;
   fixed_coords<typename P::S0, P::WBITS>(tid, xf, yf);
@@ -156,6 +180,7 @@ __device__ __forceinline__ void fft_forward(float2 (&v)[P::E], float2* tile, con
   stage_load<typename P::S1, P>(v, tile, xf, yf);
   stage_compute<typename P::S1, false>(v, xf, yf, tw + TL::X1, tw + TL::Y1);
   stage_store<typename P::S1, P>(v, tile, xf, yf);
+  pre();
   __syncthreads();
   fixed_coords<typename P::S2, P::WBITS>(tid, xf, yf);
   stage_load<typename P::S2, P>(v, tile, xf, yf);
@@ -234,20 +259,22 @@ __device__ __forceinline__ void frame_store_cross(const float2 (&v)[P::E], const
 
 // forward only: fwd operator, intensities, line-search costs.  `zero`: the pattern is skipped,
 // its far field is identically 0 and point() is evaluated on zeros without any transform.
-template <class P, class Gather, class Point>
-__device__ __forceinline__ void spectrum_pass(const Cta<P>& c, bool zero, Gather gather, Point point) {
+template <class P, class Gather, class Pre, class Point>
+__device__ __forceinline__ void spectrum_pass(const Cta<P>& c, bool zero, Gather gather, Pre pre,
+                                              Point point) {
   float2 v[P::E];
   if (zero) {
     for (int k1 = 0; k1 < P::RC; ++k1) {
 #pragma unroll
       for (int e = 0; e < P::E; ++e) v[e] = make_float2(0.f, 0.f);
+      pre(k1);
       point(k1, v);
     }
     return;
   }
   if (P::RC == 1) {
     gather(0, v);
-    fft_forward<P>(v, c.tile, c.tw, c.tid);
+    fft_forward<P>(v, c.tile, c.tw, c.tid, [&]() { pre(0); });
     point(0, v);
     __syncthreads();
   } else {
@@ -259,7 +286,7 @@ __device__ __forceinline__ void spectrum_pass(const Cta<P>& c, bool zero, Gather
     __syncthreads();
     for (int k1 = 0; k1 < P::RC; ++k1) {
       frame_load_s0<P>(v, c, k1);
-      fft_forward<P>(v, c.tile, c.tw, c.tid);
+      fft_forward<P>(v, c.tile, c.tw, c.tid, [&]() { pre(k1); });
       point(k1, v);
       __syncthreads();
     }
@@ -267,12 +294,13 @@ __device__ __forceinline__ void spectrum_pass(const Cta<P>& c, bool zero, Gather
 }
 
 // forward -> pointwise -> inverse with the spectrum kept in registers (the fused gradient)
-template <class P, class Gather, class Point, class Near>
-__device__ __forceinline__ void fused_pass(const Cta<P>& c, Gather gather, Point point, Near near) {
+template <class P, class Gather, class Pre, class Point, class Near>
+__device__ __forceinline__ void fused_pass(const Cta<P>& c, Gather gather, Pre pre, Point point,
+                                           Near near) {
   float2 v[P::E];
   if (P::RC == 1) {
     gather(0, v);
-    fft_forward<P>(v, c.tile, c.tw, c.tid);
+    fft_forward<P>(v, c.tile, c.tw, c.tid, [&]() { pre(0); });
     point(0, v);
     fft_inverse<P>(v, c.tile, c.tw, c.tid);
     near(0, v);
@@ -285,7 +313,7 @@ __device__ __forceinline__ void fused_pass(const Cta<P>& c, Gather gather, Point
     __syncthreads();
     for (int k1 = 0; k1 < P::RC; ++k1) {
       frame_load_s0<P>(v, c, k1);
-      fft_forward<P>(v, c.tile, c.tw, c.tid);
+      fft_forward<P>(v, c.tile, c.tw, c.tid, [&]() { pre(k1); });
       point(k1, v);
       fft_inverse<P>(v, c.tile, c.tw, c.tid);
       frame_store_s0<P>(v, c, k1);  // the positions this thread loaded: no hazard
@@ -334,11 +362,11 @@ __device__ __forceinline__ void inverse_pass(const Cta<P>& c, Load load, Near ne
 // (red.global.add.v2.f32) per object pixel instead of the reference's 8 scalar atomics per probe
 // pixel (kernels.cu:73-80).  The column to the right of the block only receives the gam * t part
 // (the neighbouring block adds its own share: the adds commute).  Leaves the tile free (trailing barrier).
-template <class P>
-__device__ __forceinline__ void scatter_block(float2 (&v)[P::E], const Cta<P>& c, int cb,
-                                              const float2* __restrict__ prb, float scale,
-                                              float2* __restrict__ grad_t, const Geo& g,
-                                              const Pat& p) {
+template <class P, bool FULL>
+__device__ __forceinline__ void scatter_impl(float2 (&v)[P::E], const Cta<P>& c, int cb,
+                                             const float2* __restrict__ prb, float scale,
+                                             float2* __restrict__ grad_t, const Geo& g,
+                                             const Pat& p) {
   constexpr int ROWS = P::N, COLS = Cross<P>::CW;
   constexpr int PITCH = TileGeom<P>::WORDS / ROWS;
   constexpr int RUN = ROWS * COLS / P::NT;  // 32 output rows per thread
@@ -349,9 +377,9 @@ __device__ __forceinline__ void scatter_block(float2 (&v)[P::E], const Cta<P>& c
   for (int e = 0; e < P::E; ++e) {
     int y, x;
     nat_coord<P>(c, cb, e, y, x);
-    const int iy = y - g.o, ix = x - g.o;
+    const int iy = FULL ? y : y - g.o, ix = FULL ? x : x - g.o;
     float2 t = make_float2(0.f, 0.f);
-    if ((unsigned)iy < (unsigned)g.P && (unsigned)ix < (unsigned)g.P) {
+    if (FULL || ((unsigned)iy < (unsigned)g.P && (unsigned)ix < (unsigned)g.P)) {
       const float2 pr = __ldg(prb + iy * g.P + ix);
       t.x = scale * (pr.x * v[e].x + pr.y * v[e].y);  // conj(prb) * near
       t.y = scale * (pr.x * v[e].y - pr.y * v[e].x);
@@ -397,28 +425,47 @@ __device__ __forceinline__ void scatter_block(float2 (&v)[P::E], const Cta<P>& c
   }
   __syncthreads();
 }
+template <class P>
+__device__ __forceinline__ void scatter_block(float2 (&v)[P::E], const Cta<P>& c, int cb,
+                                              const float2* __restrict__ prb, float scale,
+                                              float2* __restrict__ grad_t, const Geo& g,
+                                              const Pat& p) {
+  if (g.P == P::N)
+    scatter_impl<P, true>(v, c, cb, prb, scale, grad_t, g, p);
+  else
+    scatter_impl<P, false>(v, c, cb, prb, scale, grad_t, g, p);
+}
 
 // ---------------------------------------------------------------- probe adjoint
 // thread-private accumulators in L2-resident scratch: acc[(cb*E + e)*NT + tid], natural ownership.
 // acc += scale * near * conj(patch)                                    (kernels.cu:82-94)
-template <class P>
-__device__ __forceinline__ void pacc_add(float2 (&v)[P::E], const Cta<P>& c, int cb,
-                                         const float2* __restrict__ psi_t, float scale,
-                                         const Geo& g, const Pat& p) {
+template <class P, bool FULL, bool INSIDE>
+__device__ __forceinline__ void pacc_impl(float2 (&v)[P::E], const Cta<P>& c, int cb,
+                                          const float2* __restrict__ psi_t, float scale,
+                                          const Geo& g, const Pat& p) {
   float2* acc = c.stash + (size_t)cb * P::E * P::NT + c.tid;
 #pragma unroll
   for (int e = 0; e < P::E; ++e) {
     int y, x;
     nat_coord<P>(c, cb, e, y, x);
-    const int iy = y - g.o, ix = x - g.o;
-    if ((unsigned)iy < (unsigned)g.P && (unsigned)ix < (unsigned)g.P) {
-      const float2 f = patch_at(psi_t, g, p, iy, ix);
+    const int iy = FULL ? y : y - g.o, ix = FULL ? x : x - g.o;
+    if (FULL || ((unsigned)iy < (unsigned)g.P && (unsigned)ix < (unsigned)g.P)) {
+      const float2 f = patch_at<INSIDE>(psi_t, g, p, iy, ix);
       float2 s = acc[e * P::NT];
       s.x += scale * (v[e].x * f.x + v[e].y * f.y);
       s.y += scale * (v[e].y * f.x - v[e].x * f.y);
       acc[e * P::NT] = s;
     }
   }
+}
+template <class P>
+__device__ __forceinline__ void pacc_add(float2 (&v)[P::E], const Cta<P>& c, int cb,
+                                         const float2* __restrict__ psi_t, float scale,
+                                         const Geo& g, const Pat& p) {
+  if (g.P == P::N && p.inside)
+    pacc_impl<P, true, true>(v, c, cb, psi_t, scale, g, p);
+  else
+    pacc_impl<P, false, false>(v, c, cb, psi_t, scale, g, p);
 }
 template <class P>
 __device__ __forceinline__ void pacc_zero(const Cta<P>& c) {

@@ -40,17 +40,25 @@ __device__ __forceinline__ void cta_setup(Cta<P>& c, unsigned char* raw, const P
   c.accp = reinterpret_cast<float*>(c.stash + Scratch<P>::STASH);
   fixed_coords<typename P::S0, P::WBITS>(c.tid, c.xf0, c.yf0);
   fixed_coords<typename P::S2, P::WBITS>(c.tid, c.xf2, c.yf2);
+  c.sbase = spec_base<P>(c.xf2, c.yf2);
   __syncthreads();
 }
 
 // Square root / division without the IEEE slow-path subroutine calls: MUFU.RSQ / MUFU.RCP plus one
 // Newton step, accurate to ~1 ulp for the non-negative, normal-range inputs of this path.
 __device__ __forceinline__ float fsqrt(float x) {
-  if (x < 1e-35f) return 0.f;
-  const float r = rsqrtf(x);
+  const float r = rsqrtf(fmaxf(x, 1e-35f));
   float s = x * r;                        // ~sqrt(x)
   s = fmaf(fmaf(-s, s, x), 0.5f * r, s);  // one Newton step
-  return s;
+  return x < 1e-35f ? 0.f : s;            // branch-free (a select)
+}
+
+// pull the next pattern's measured-data tile into L2 while this one is being transformed
+template <class P>
+__device__ __forceinline__ void prefetch_l2(const float* d, int tid) {
+  constexpr int LINES = P::N * P::N / 32;  // 128-byte lines
+  for (int i = tid; i < LINES; i += P::NT)
+    asm volatile("prefetch.global.L2 [%0];" ::"l"(d + (size_t)i * 32));
 }
 __device__ __forceinline__ float fdiv(float a, float b) {
   const float r = __frcp_rn(b);
@@ -88,6 +96,7 @@ __global__ void __launch_bounds__(P::NT) k_fwd(const PassArgs a) {
     const float2* prb_t = a.prb + (size_t)t * a.prb_ts;
     spectrum_pass<P>(
         c, p.skip, [&](int cb, float2(&v)[P::E]) { gather_nat<P>(v, c, cb, psi_t, prb_t, g, p); },
+        [](int) {},
         [&](int k1, float2(&v)[P::E]) {
 #pragma unroll
           for (int e = 0; e < P::E; ++e) out[spec_index<P>(c, k1, e)] = v[e];
@@ -187,12 +196,20 @@ __global__ void __launch_bounds__(P::NT) k_intensity(const PassArgs a) {
     const float* d = a.data + (size_t)pat * P::N * P::N;
     float* io = a.inten_out ? a.inten_out + (size_t)pat * P::N * P::N : nullptr;
     float sa = 0.f, sb = 0.f, scost = 0.f;
+    if (pat + (int)gridDim.x < npat) prefetch_l2<P>(d + (size_t)gridDim.x * P::N * P::N, c.tid);
     const int kfirst = p.skip ? a.nmodes - 1 : 0;  // a skipped pattern has I = 0: one zero pass
     for (int k = kfirst; k < a.nmodes; ++k) {
       const float2* prb_k = a.prb + (size_t)t * a.prb_ts + (size_t)k * a.prb_ms;
       const bool first = (k == kfirst), last = (k + 1 == a.nmodes);
+      float dreg[P::E];
       spectrum_pass<P>(
           c, p.skip, [&](int cb, float2(&v)[P::E]) { gather_nat<P>(v, c, cb, psi_t, prb_k, g, p); },
+          [&](int k1) {
+            if (last) {
+#pragma unroll
+              for (int e = 0; e < P::E; ++e) dreg[e] = __ldg(d + spec_index<P>(c, k1, e));
+            }
+          },
           [&](int k1, float2(&v)[P::E]) {
             float* ia = c.accp + (size_t)k1 * P::E * P::NT + c.tid;
 #pragma unroll
@@ -203,7 +220,7 @@ __global__ void __launch_bounds__(P::NT) k_intensity(const PassArgs a) {
                 ia[e * P::NT] = I;
               } else {
                 const int idx = spec_index<P>(c, k1, e);
-                const float dd = __ldg(d + idx);
+                const float dd = dreg[e];
                 sa += fsqrt(I * dd);
                 sb += I;
                 scost += minf_px<MODEL>(I * iscale, dd, fsqrt(dd));
@@ -247,13 +264,19 @@ __global__ void __launch_bounds__(P::NT) k_grad(const PassArgs a) {
     float2* grad_t = a.grad + (size_t)t * g.nz * g.n;
     const float* d = a.data + (size_t)pat * P::N * P::N;
     const float* ii = a.inten_in ? a.inten_in + (size_t)pat * P::N * P::N : nullptr;
+    if (pat + (int)gridDim.x < npat) prefetch_l2<P>(d + (size_t)gridDim.x * P::N * P::N, c.tid);
+    float dreg[P::E];
     fused_pass<P>(
         c, [&](int cb, float2(&v)[P::E]) { gather_nat<P>(v, c, cb, psi_t, prb_t, g, p); },
+        [&](int k1) {
+#pragma unroll
+          for (int e = 0; e < P::E; ++e) dreg[e] = __ldg(d + spec_index<P>(c, k1, e));
+        },
         [&](int k1, float2(&v)[P::E]) {
 #pragma unroll
           for (int e = 0; e < P::E; ++e) {
             const int idx = spec_index<P>(c, k1, e);
-            const float dd = __ldg(d + idx);
+            const float dd = dreg[e];
             const float I = ii ? __ldg(ii + idx) * iscale : (v[e].x * v[e].x + v[e].y * v[e].y);
             float f;
             if (MODEL == PTX_MODEL_GAUSSIAN)
@@ -301,12 +324,15 @@ __global__ void __launch_bounds__(P::NT) k_linesearch(const PassArgs a) {
     float cost[9];
 #pragma unroll
     for (int q = 0; q < 9; ++q) cost[q] = 0.f;
+    float dreg[P::E];
+    if (pat + (int)gridDim.x < npat) prefetch_l2<P>(d + (size_t)gridDim.x * NN, c.tid);
     for (int j = 0; j < a.npairs; ++j) {
       const float2* prb_a = a.prb + (size_t)t * a.prb_ts + (size_t)j * a.prb_ms;
       const float2* prb_b = a.prb_b + (size_t)t * a.prb_b_ts + (size_t)j * a.prb_b_ms;
       const bool first = (j == 0), last = (j + 1 == a.npairs);
       spectrum_pass<P>(
           c, p.skip, [&](int cb, float2(&v)[P::E]) { gather_nat<P>(v, c, cb, psi_a, prb_a, g, p); },
+          [](int) {},
           [&](int k1, float2(&v)[P::E]) {
             float2* st = c.stash + (size_t)k1 * P::E * P::NT + c.tid;
 #pragma unroll
@@ -314,6 +340,12 @@ __global__ void __launch_bounds__(P::NT) k_linesearch(const PassArgs a) {
           });
       spectrum_pass<P>(
           c, p.skip, [&](int cb, float2(&v)[P::E]) { gather_nat<P>(v, c, cb, psi_b, prb_b, g, p); },
+          [&](int k1) {
+            if (last) {
+#pragma unroll
+              for (int e = 0; e < P::E; ++e) dreg[e] = __ldg(d + spec_index<P>(c, k1, e));
+            }
+          },
           [&](int k1, float2(&v)[P::E]) {
             const float2* st = c.stash + (size_t)k1 * P::E * P::NT + c.tid;
             float* ap = c.accp + (size_t)k1 * P::E * P::NT + c.tid;
@@ -338,7 +370,7 @@ __global__ void __launch_bounds__(P::NT) k_linesearch(const PassArgs a) {
               }
               if (last) {
                 const int idx = spec_index<P>(c, k1, e);
-                const float dd = __ldg(d + idx);
+                const float dd = dreg[e];
                 const float sqd = fsqrt(dd);
                 if (p1in) q1 = __ldg(p1in + idx);
                 cost[0] += minf_px<MODEL>(q1, dd, sqd);
