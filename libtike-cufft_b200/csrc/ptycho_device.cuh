@@ -89,7 +89,8 @@ template <class P>
 struct Cta {
   float2* tile;        // shared: NY x (NX+4) complex
   const float2* tw;    // shared twiddle tables
-  double* red;         // shared reduction slots
+  double* red;         // shared cross-warp reduction scratch
+  double* slots;       // shared per-thread running sums: slots[k * NT], k < 9
   float2* frame;       // global scratch frame [RC][NY][NX] (RC > 1 only)
   float2* stash;       // global thread-private scratch, N*N complex: [(k*E + e)*NT + tid]
   float* accp;         // global thread-private scratch, 3*N*N floats
@@ -367,61 +368,74 @@ __device__ __forceinline__ void scatter_impl(float2 (&v)[P::E], const Cta<P>& c,
                                              const float2* __restrict__ prb, float scale,
                                              float2* __restrict__ grad_t, const Geo& g,
                                              const Pat& p) {
+  // FULL: probe window == frame and the (P+1)^2 footprint lies inside the object: no predicates.
   constexpr int ROWS = P::N, COLS = Cross<P>::CW;
   constexpr int PITCH = TileGeom<P>::WORDS / ROWS;
   constexpr int RUN = ROWS * COLS / P::NT;  // 32 output rows per thread
-  static_assert(PITCH >= COLS, "scatter block must fit the tile");
+  static_assert(PITCH >= COLS + 1, "scatter block (+ one zero column) must fit the tile");
+  static_assert(ROWS <= P::NT, "one thread per row zeroes the left guard column");
   float2* tile = c.tile;
+  const float2 z = make_float2(0.f, 0.f);
   __syncthreads();  // other threads may still be reading the tile (last inverse stage)
+  // block layout: row y at tile[y*PITCH], column 0 = zero guard (left neighbour of the block's first
+  // column, owned by the previous block), column 1 + xl = t[y][xl]
 #pragma unroll
   for (int e = 0; e < P::E; ++e) {
     int y, x;
     nat_coord<P>(c, cb, e, y, x);
     const int iy = FULL ? y : y - g.o, ix = FULL ? x : x - g.o;
-    float2 t = make_float2(0.f, 0.f);
+    float2 t = z;
     if (FULL || ((unsigned)iy < (unsigned)g.P && (unsigned)ix < (unsigned)g.P)) {
       const float2 pr = __ldg(prb + iy * g.P + ix);
       t.x = scale * (pr.x * v[e].x + pr.y * v[e].y);  // conj(prb) * near
       t.y = scale * (pr.x * v[e].y - pr.y * v[e].x);
     }
-    tile[y * PITCH + (x - cb * COLS)] = t;
+    tile[y * PITCH + 1 + (x - cb * COLS)] = t;
   }
+  if (c.tid < ROWS) tile[c.tid * PITCH] = z;
   __syncthreads();
   const int xl = c.tid % COLS, r0 = (c.tid / COLS) * RUN;
-  const int x = cb * COLS + xl;                   // frame column of this thread's outputs
-  const int oc = p.C + x - g.o;                   // object column
-  const bool colok = (x >= g.o) && (x <= g.o + g.P) && (oc < g.n);
-  // the extra column right of the block: x + 1, fed by gam * t[.][xl] only
-  const bool extra = (xl == COLS - 1);
-  const bool ecolok = extra && (x + 1 >= g.o) && (x + 1 <= g.o + g.P) && (oc + 1 < g.n);
+  const int x = cb * COLS + xl;                    // frame column of this thread's outputs
+  const int oc = p.C + x - (FULL ? 0 : g.o);       // object column
   const float a0 = 1.f - p.gam, a1 = p.gam, b0 = 1.f - p.rho, b1 = p.rho;
-  float2 hp = make_float2(0.f, 0.f), ep = make_float2(0.f, 0.f);
-  if (r0 > 0) {
-    const float2 tc = tile[(r0 - 1) * PITCH + xl];
-    const float2 tl = xl > 0 ? tile[(r0 - 1) * PITCH + xl - 1] : make_float2(0.f, 0.f);
-    hp = make_float2(a0 * tc.x + a1 * tl.x, a0 * tc.y + a1 * tl.y);
-    ep = make_float2(a1 * tc.x, a1 * tc.y);
+  {
+    const bool colok = FULL || ((x >= g.o) && (x <= g.o + g.P) && (oc < g.n));
+    const float2* tp = tile + r0 * PITCH + xl;  // tp[0] = left tap, tp[1] = centre tap of row r0
+    float2 hp = z;
+    if (r0 > 0) {
+      const float2 tl = tp[-PITCH], tc = tp[1 - PITCH];
+      hp = make_float2(a0 * tc.x + a1 * tl.x, a0 * tc.y + a1 * tl.y);
+    }
+    const int orow0 = p.R + r0 - (FULL ? 0 : g.o);
+    float2* dst = grad_t + (ptrdiff_t)orow0 * g.n + oc;
+#pragma unroll 8
+    for (int i = 0; i < RUN; ++i) {
+      const float2 tl = tp[i * PITCH], tc = tp[i * PITCH + 1];
+      const float2 hc = make_float2(a0 * tc.x + a1 * tl.x, a0 * tc.y + a1 * tl.y);
+      const float2 out = make_float2(b0 * hc.x + b1 * hp.x, b0 * hc.y + b1 * hp.y);
+      const int y = r0 + i;
+      if (FULL || (colok && (y >= g.o) && (y <= g.o + g.P) && (orow0 + i < g.nz)))
+        atomicAdd(dst + (ptrdiff_t)i * g.n, out);
+      hp = hc;
+    }
+    if (r0 + RUN == ROWS) {  // the last run also emits row ROWS (only the rho * h[ROWS-1] share)
+      if (FULL || (colok && (ROWS <= g.o + g.P) && (orow0 + RUN < g.nz)))
+        atomicAdd(dst + (ptrdiff_t)RUN * g.n, make_float2(b1 * hp.x, b1 * hp.y));
+    }
   }
-  const int rlast = (r0 + RUN == ROWS) ? RUN + 1 : RUN;  // the last run also emits row ROWS
-#pragma unroll 4
-  for (int i = 0; i < rlast; ++i) {
-    const int y = r0 + i;
-    float2 hc = make_float2(0.f, 0.f), ec = make_float2(0.f, 0.f);
-    if (y < ROWS) {
-      const float2 tc = tile[y * PITCH + xl];
-      const float2 tl = xl > 0 ? tile[y * PITCH + xl - 1] : make_float2(0.f, 0.f);
-      hc = make_float2(a0 * tc.x + a1 * tl.x, a0 * tc.y + a1 * tl.y);
-      ec = make_float2(a1 * tc.x, a1 * tc.y);
+  // the column right of the block, x = (cb+1)*COLS, receives only the gam * t[.][COLS-1] share
+  if (c.tid < 32) {
+    const int xe = (cb + 1) * COLS;
+    const int oce = p.C + xe - (FULL ? 0 : g.o);
+    const bool colok = FULL || ((xe >= g.o) && (xe <= g.o + g.P) && (oce < g.n));
+    for (int y = c.tid; y <= ROWS; y += 32) {
+      const float2 tc = y < ROWS ? tile[y * PITCH + COLS] : z;
+      const float2 tu = y > 0 ? tile[(y - 1) * PITCH + COLS] : z;
+      const int orow = p.R + y - (FULL ? 0 : g.o);
+      if (FULL || (colok && (y >= g.o) && (y <= g.o + g.P) && (orow < g.nz)))
+        atomicAdd(grad_t + (ptrdiff_t)orow * g.n + oce,
+                  make_float2(a1 * (b0 * tc.x + b1 * tu.x), a1 * (b0 * tc.y + b1 * tu.y)));
     }
-    const int orow = p.R + y - g.o;
-    const bool rowok = (y >= g.o) && (y <= g.o + g.P) && (orow < g.nz);
-    if (rowok) {
-      float2* dst = grad_t + (size_t)orow * g.n + oc;
-      if (colok) atomicAdd(dst, make_float2(b0 * hc.x + b1 * hp.x, b0 * hc.y + b1 * hp.y));
-      if (ecolok) atomicAdd(dst + 1, make_float2(b0 * ec.x + b1 * ep.x, b0 * ec.y + b1 * ep.y));
-    }
-    hp = hc;
-    ep = ec;
   }
   __syncthreads();
 }
@@ -430,7 +444,7 @@ __device__ __forceinline__ void scatter_block(float2 (&v)[P::E], const Cta<P>& c
                                               const float2* __restrict__ prb, float scale,
                                               float2* __restrict__ grad_t, const Geo& g,
                                               const Pat& p) {
-  if (g.P == P::N)
+  if (g.P == P::N && p.inside)
     scatter_impl<P, true>(v, c, cb, prb, scale, grad_t, g, p);
   else
     scatter_impl<P, false>(v, c, cb, prb, scale, grad_t, g, p);

@@ -14,8 +14,10 @@ template <class P>
 struct Smem {
   static constexpr int TILE = TileGeom<P>::WORDS;  // float2
   static constexpr int TW = TwLayout<P>::TOTAL;    // float2
-  static constexpr int RED = (P::NT / 32) * 12;    // doubles
-  static constexpr size_t BYTES = (size_t)(TILE + TW) * sizeof(float2) + RED * sizeof(double);
+  static constexpr int RED = (P::NT / 32) * 12;    // doubles: cross-warp reduction scratch
+  static constexpr int SLOTS = 9 * P::NT;          // doubles: per-thread running sums [k][tid]
+  static constexpr size_t BYTES =
+      (size_t)(TILE + TW) * sizeof(float2) + (size_t)(RED + SLOTS) * sizeof(double);
 };
 
 template <class P>
@@ -32,6 +34,9 @@ __device__ __forceinline__ void cta_setup(Cta<P>& c, unsigned char* raw, const P
   c.tile = reinterpret_cast<float2*>(raw);
   float2* tw = c.tile + Smem<P>::TILE;
   c.red = reinterpret_cast<double*>(tw + Smem<P>::TW);
+  c.slots = c.red + Smem<P>::RED + c.tid;  // this thread's running sums: slots[k * NT]
+#pragma unroll
+  for (int k = 0; k < 9; ++k) c.slots[k * P::NT] = 0.0;
   for (int i = c.tid; i < Smem<P>::TW; i += P::NT) tw[i] = a.tw[i];
   c.tw = tw;
   float2* scr = a.scratch + (size_t)blockIdx.x * a.scratch_per_cta;
@@ -44,13 +49,26 @@ __device__ __forceinline__ void cta_setup(Cta<P>& c, unsigned char* raw, const P
   __syncthreads();
 }
 
-// Square root / division without the IEEE slow-path subroutine calls: MUFU.RSQ / MUFU.RCP plus one
-// Newton step, accurate to ~1 ulp for the non-negative, normal-range inputs of this path.
-__device__ __forceinline__ float fsqrt(float x) {
-  const float r = rsqrtf(fmaxf(x, 1e-35f));
-  float s = x * r;                        // ~sqrt(x)
-  s = fmaf(fmaf(-s, s, x), 0.5f * r, s);  // one Newton step
-  return x < 1e-35f ? 0.f : s;            // branch-free (a select)
+// Square roots / reciprocals through the SFU (MUFU.RSQ / MUFU.RCP, <= 2 ulp) instead of the IEEE
+// slow-path subroutines: a handful of instructions per pixel, and a relative error (2.4e-7) far
+// below the 1e-5 operator bar.  Arguments are clamped at 1e-35 so that exact zeros stay finite.
+__device__ __forceinline__ float frsq(float x) { return rsqrtf(fmaxf(x, 1e-35f)); }
+__device__ __forceinline__ float fsqrt(float x) { return x * frsq(x); }  // 0 -> 0
+__device__ __forceinline__ float frcp(float x) {
+  float r;
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
+  return r;
+}
+
+// residual factor of one far-field pixel (ptycho.py:353, 360): the residual is F * factor
+//   gaussian: fscale * (1 - sqrt(d) / (sqrt(I) + 1e-32)) = fscale - fscale * d * rsqrt(d * I)
+//   poisson:  fscale * (1 - d / (I + 1e-32))
+template <int MODEL>
+__device__ __forceinline__ float residual_factor(float d, float I, float fscale) {
+  if (MODEL == PTX_MODEL_GAUSSIAN)
+    return fmaf(-(fscale * d), frsq(d * I), fscale);
+  else
+    return fmaf(-(fscale * d), frcp(I + 1e-32f), fscale);
 }
 
 // pull the next pattern's measured-data tile into L2 while this one is being transformed
@@ -59,11 +77,6 @@ __device__ __forceinline__ void prefetch_l2(const float* d, int tid) {
   constexpr int LINES = P::N * P::N / 32;  // 128-byte lines
   for (int i = tid; i < LINES; i += P::NT)
     asm volatile("prefetch.global.L2 [%0];" ::"l"(d + (size_t)i * 32));
-}
-__device__ __forceinline__ float fdiv(float a, float b) {
-  const float r = __frcp_rn(b);
-  const float q = a * r;
-  return fmaf(fmaf(-q, b, a), r, q);
 }
 
 // minimisation functional per pixel (ptycho.py:308-314), x = intensity estimate, d = data
@@ -187,7 +200,6 @@ __global__ void __launch_bounds__(P::NT) k_intensity(const PassArgs a) {
   cta_setup<P>(c, smem_raw, a);
   const Geo g = a.g;
   const float iscale = a.sc ? a.sc[0] : 1.f;
-  double acc[3] = {0.0, 0.0, 0.0};
   const int npat = g.T * g.S;
   for (int pat = blockIdx.x; pat < npat; pat += gridDim.x) {
     const int t = pat / g.S;
@@ -195,7 +207,6 @@ __global__ void __launch_bounds__(P::NT) k_intensity(const PassArgs a) {
     const float2* psi_t = a.psi + (size_t)t * g.nz * g.n;
     const float* d = a.data + (size_t)pat * P::N * P::N;
     float* io = a.inten_out ? a.inten_out + (size_t)pat * P::N * P::N : nullptr;
-    float sa = 0.f, sb = 0.f, scost = 0.f;
     if (pat + (int)gridDim.x < npat) prefetch_l2<P>(d + (size_t)gridDim.x * P::N * P::N, c.tid);
     const int kfirst = p.skip ? a.nmodes - 1 : 0;  // a skipped pattern has I = 0: one zero pass
     for (int k = kfirst; k < a.nmodes; ++k) {
@@ -204,14 +215,13 @@ __global__ void __launch_bounds__(P::NT) k_intensity(const PassArgs a) {
       float dreg[P::E];
       spectrum_pass<P>(
           c, p.skip, [&](int cb, float2(&v)[P::E]) { gather_nat<P>(v, c, cb, psi_t, prb_k, g, p); },
-          [&](int k1) {
-            if (last) {
+          [&](int k1) {  // unconditional: a conditionally filled array would live in local memory
 #pragma unroll
-              for (int e = 0; e < P::E; ++e) dreg[e] = __ldg(d + spec_index<P>(c, k1, e));
-            }
+            for (int e = 0; e < P::E; ++e) dreg[e] = __ldg(d + spec_index<P>(c, k1, e));
           },
           [&](int k1, float2(&v)[P::E]) {
             float* ia = c.accp + (size_t)k1 * P::E * P::NT + c.tid;
+            float sa = 0.f, sb = 0.f, scost = 0.f;  // fp32 over 32 pixels, double across tiles
 #pragma unroll
             for (int e = 0; e < P::E; ++e) {
               float I = v[e].x * v[e].x + v[e].y * v[e].y;
@@ -227,12 +237,17 @@ __global__ void __launch_bounds__(P::NT) k_intensity(const PassArgs a) {
                 if (io) io[idx] = I;
               }
             }
+            if (last) {
+              c.slots[0 * P::NT] += (double)sa;
+              c.slots[1 * P::NT] += (double)sb;
+              c.slots[2 * P::NT] += (double)scost;
+            }
           });
     }
-    acc[0] += (double)sa;
-    acc[1] += (double)sb;
-    acc[2] += (double)scost;
   }
+  double acc[3];
+#pragma unroll
+  for (int k = 0; k < 3; ++k) acc[k] = c.slots[k * P::NT];
   block_reduce_add<3, P::NT / 32>(acc, c.red, a.red, c.tid);
 }
 
@@ -278,11 +293,7 @@ __global__ void __launch_bounds__(P::NT) k_grad(const PassArgs a) {
             const int idx = spec_index<P>(c, k1, e);
             const float dd = dreg[e];
             const float I = ii ? __ldg(ii + idx) * iscale : (v[e].x * v[e].x + v[e].y * v[e].y);
-            float f;
-            if (MODEL == PTX_MODEL_GAUSSIAN)
-              f = fscale * (1.f - fdiv(fsqrt(dd), fsqrt(I) + 1e-32f));
-            else
-              f = fscale * (1.f - fdiv(dd, I + 1e-32f));
+            const float f = residual_factor<MODEL>(dd, I, fscale);
             v[e].x *= f;
             v[e].y *= f;
           }
@@ -309,9 +320,6 @@ __global__ void __launch_bounds__(P::NT) k_linesearch(const PassArgs a) {
   cta_setup<P>(c, smem_raw, a);
   const Geo g = a.g;
   constexpr size_t NN = (size_t)P::N * P::N;
-  double acc[9];
-#pragma unroll
-  for (int q = 0; q < 9; ++q) acc[q] = 0.0;
   const bool multi = a.npairs > 1;
   const int npat = g.T * g.S;
   for (int pat = blockIdx.x; pat < npat; pat += gridDim.x) {
@@ -321,9 +329,6 @@ __global__ void __launch_bounds__(P::NT) k_linesearch(const PassArgs a) {
     const float* p1in = a.inten_in ? a.inten_in + (size_t)pat * NN : nullptr;
     const float2* psi_a = a.psi + (size_t)t * g.nz * g.n;
     const float2* psi_b = a.psi_b + (size_t)t * g.nz * g.n;
-    float cost[9];
-#pragma unroll
-    for (int q = 0; q < 9; ++q) cost[q] = 0.f;
     float dreg[P::E];
     if (pat + (int)gridDim.x < npat) prefetch_l2<P>(d + (size_t)gridDim.x * NN, c.tid);
     for (int j = 0; j < a.npairs; ++j) {
@@ -340,15 +345,17 @@ __global__ void __launch_bounds__(P::NT) k_linesearch(const PassArgs a) {
           });
       spectrum_pass<P>(
           c, p.skip, [&](int cb, float2(&v)[P::E]) { gather_nat<P>(v, c, cb, psi_b, prb_b, g, p); },
-          [&](int k1) {
-            if (last) {
+          [&](int k1) {  // unconditional: a conditionally filled array would live in local memory
 #pragma unroll
-              for (int e = 0; e < P::E; ++e) dreg[e] = __ldg(d + spec_index<P>(c, k1, e));
-            }
+            for (int e = 0; e < P::E; ++e) dreg[e] = __ldg(d + spec_index<P>(c, k1, e));
           },
           [&](int k1, float2(&v)[P::E]) {
             const float2* st = c.stash + (size_t)k1 * P::E * P::NT + c.tid;
             float* ap = c.accp + (size_t)k1 * P::E * P::NT + c.tid;
+            float cost[9];  // fp32 over 32 pixels, double across tiles (per-thread smem slots)
+#pragma unroll
+            for (int q = 0; q < 9; ++q) cost[q] = 0.f;
+            const float gam0 = exp2f(-(float)a.c0);
 #pragma unroll
             for (int e = 0; e < P::E; ++e) {
               const float2 t1 = st[e * P::NT];
@@ -374,18 +381,24 @@ __global__ void __launch_bounds__(P::NT) k_linesearch(const PassArgs a) {
                 const float sqd = fsqrt(dd);
                 if (p1in) q1 = __ldg(p1in + idx);
                 cost[0] += minf_px<MODEL>(q1, dd, sqd);
-                float gam = exp2f(-(float)a.c0);
-                for (int q = 0; q < a.ncand; ++q) {
-                  cost[1 + q] += minf_px<MODEL>(q1 + gam * gam * q2 + gam * q3, dd, sqd);
+                float gam = gam0;
+#pragma unroll
+                for (int q = 0; q < 8; ++q) {
+                  if (q < a.ncand) cost[1 + q] += minf_px<MODEL>(q1 + gam * gam * q2 + gam * q3, dd, sqd);
                   gam *= 0.5f;
                 }
               }
             }
+            if (last) {
+#pragma unroll
+              for (int q = 0; q < 9; ++q) c.slots[q * P::NT] += (double)cost[q];
+            }
           });
     }
-#pragma unroll
-    for (int q = 0; q < 9; ++q) acc[q] += (double)cost[q];
   }
+  double acc[9];
+#pragma unroll
+  for (int q = 0; q < 9; ++q) acc[q] = c.slots[q * P::NT];
   block_reduce_add<9, P::NT / 32>(acc, c.red, a.red, c.tid);
 }
 
