@@ -407,10 +407,13 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--workload", default="c2", choices=["c2", "c4"])
-    ap.add_argument("--angles", type=int, default=8, help="angles per GPU per step")
+    ap.add_argument("--angles", type=int, default=0,
+                    help="angles per GPU per step (default: 8 for c2, 2 for c4 = 512 MiB of data)")
     ap.add_argument("--no-cg", action="store_true")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3)
+    if args.angles <= 0:
+        args.angles = 8 if args.workload == "c2" else 2
     if args.impl == "reference":
         rank = int(os.environ.get("RANK", "0"))
         world = int(os.environ.get("WORLD_SIZE", "1"))

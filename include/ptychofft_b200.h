@@ -118,8 +118,9 @@ int ptx_cg_grad(ptx_plan* p, int what, const void* psi, const void* scan, const 
 /* ptycho.py:383-393 (object, npairs = nmodes) and 451-461 (probe, npairs = 1):
  *   for each pair j: t1 = fwd(obj_a, prb_a[:,ja]) ; t2 = fwd(obj_b, prb_b[:,jb])
  *   p1 += |t1|^2 ; p2 += |t2|^2 ; p3 += 2 Re(t1 conj t2)      (p1 = p1_in when given)
- *   cost[0] += minf(p1) ; cost[1+c] += minf(p1 + g^2 p2 + g p3), g = 2^-(c0+c), c < ncand (<= 8)
- * Pair j uses modes (mode_a0 + j, mode_b0 + j).  cost: 9 doubles (1 + 8 slots), caller-zeroed. */
+ *   cost[0] += minf(p1) ; cost[1+c] += minf(p1 + g^2 p2 + g p3), g = 2^-(c0+c), c < 4
+ * Pair j uses modes (mode_a0 + j, mode_b0 + j).  The kernel always evaluates four candidates per
+ * pass (ncand <= 4 tells how many the caller will look at).  cost: 9 doubles, caller-zeroed. */
 int ptx_cg_linesearch(ptx_plan* p, const void* obj_a, const void* prb_a, int nmodes_a, int mode_a0,
                       const void* obj_b, const void* prb_b, int nmodes_b, int mode_b0, int npairs,
                       const void* scan, const float* data, const float* p1_in, int model, int c0,

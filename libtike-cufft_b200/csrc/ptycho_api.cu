@@ -178,8 +178,9 @@ static int launch(ptx_plan* p, int kid, PassArgs& a, cudaStream_t st) {
   const int npat = a.g.T * a.g.S;
   const int grid = npat < p->grid ? npat : p->grid;
   void* params[] = {&a};
+  const bool nodata = kid == K_FWD || kid == K_NEAR || kid == K_ADJ_OBJ || kid == K_ADJ_PRB;
   cudaError_t e = cudaLaunchKernel(ops->kernels[kid], dim3(grid), dim3(ops->NT), params,
-                                   ops->smem_bytes, st);
+                                   nodata ? ops->smem_bytes_nodata : ops->smem_bytes, st);
   g_launches.fetch_add(1);
   if (e != cudaSuccess) return fail(PTX_ECUDA, "launch %s: %s", ops->names[kid], cudaGetErrorString(e));
   CUDA_TRY(cudaGetLastError());
@@ -414,7 +415,7 @@ int ptx_cg_linesearch(ptx_plan* p, const void* obj_a, const void* prb_a, int nmo
   int rc = check_plan(p);
   if (rc) return rc;
   if (!obj_a || !prb_a || !obj_b || !prb_b || !scan || !data || !cost || npairs < 1 || ncand < 1 ||
-      ncand > 8 || c0 < 0 || mode_a0 < 0 || mode_b0 < 0 || mode_a0 + npairs > nmodes_a ||
+      ncand > 4 || c0 < 0 || mode_a0 < 0 || mode_b0 < 0 || mode_a0 + npairs > nmodes_a ||
       mode_b0 + npairs > nmodes_b)
     return fail(PTX_EINVAL, "ptx_cg_linesearch: bad argument");
   PassArgs a = base_args(p);

@@ -90,13 +90,83 @@ struct Cta {
   float2* tile;        // shared: NY x (NX+4) complex
   const float2* tw;    // shared twiddle tables
   double* red;         // shared cross-warp reduction scratch
-  double* slots;       // shared per-thread running sums: slots[k * NT], k < 9
+  float* dbuf;         // shared: the measured-data tile of the current (sub-)spectrum, NY x NX f32
+  unsigned long long* bar;  // shared mbarrier: completion of the bulk copy into dbuf
+  unsigned phase;      // parity of the next completion to wait for
+  double* slots;       // global thread-private running sums: slots[k * NT], k < 9
   float2* frame;       // global scratch frame [RC][NY][NX] (RC > 1 only)
   float2* stash;       // global thread-private scratch, N*N complex: [(k*E + e)*NT + tid]
   float* accp;         // global thread-private scratch, 3*N*N floats
   int tid, xf0, yf0, xf2, yf2;
   int sbase;           // spec_index of the thread's stage-2 coordinates (element part is immediate)
+  int lbase;           // same within one sub-tile's data buffer: fy_local * N + fx
 };
+
+// ---------------------------------------------------------------- measured-data pipe (TMA bulk copy)
+// The N^2 (or, N > 128, the NY rows ky = k1 mod RC of the) measured intensities a pattern's pointwise
+// step needs are pulled into shared memory by cp.async.bulk (UBLKCP) one (sub-)tile ahead: issued
+// right after the previous tile has been consumed, waited for just before use, so the HBM latency
+// hides behind a whole inverse + forward transform.  One buffer, one mbarrier, at most one copy in
+// flight.  dp_issue must be called by all threads, after a block barrier that follows the last read
+// of the buffer.
+__device__ __forceinline__ unsigned smem_u32(const void* p) {
+  return (unsigned)__cvta_generic_to_shared(p);
+}
+template <class P>
+__device__ __forceinline__ void dp_init(Cta<P>& c) {
+  if (c.tid == 0) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(smem_u32(c.bar)));
+    asm volatile("fence.mbarrier_init.release.cluster;");
+  }
+  c.phase = 0;
+}
+template <class P>
+__device__ __forceinline__ void dp_issue(const Cta<P>& c, const float* d_pat, int k1) {
+  if (c.tid >= 32) return;
+  const unsigned bar = smem_u32(c.bar);
+  constexpr unsigned TOTAL = P::NX * P::NY * 4;
+  if (c.tid == 0) {
+    asm volatile("fence.proxy.async.shared::cta;");
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(TOTAL));
+  }
+  __syncwarp();
+  if (P::RC == 1) {
+    if (c.tid == 0)
+      asm volatile(
+          "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::
+              "r"(smem_u32(c.dbuf)), "l"(d_pat), "r"(TOTAL), "r"(bar)
+          : "memory");
+  } else {  // rows ky = k1 + RC * j of the N x N data frame, one bulk copy per row
+    for (int j = c.tid; j < P::NY; j += 32)
+      asm volatile(
+          "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::
+              "r"(smem_u32(c.dbuf + j * P::N)), "l"(d_pat + (size_t)(k1 + P::RC * j) * P::N),
+              "r"((unsigned)(P::N * 4)), "r"(bar)
+          : "memory");
+  }
+}
+template <class P>
+__device__ __forceinline__ void dp_wait(Cta<P>& c) {
+  const unsigned bar = smem_u32(c.bar);
+  unsigned done = 0;
+  while (!done) {
+    asm volatile(
+        "{\n.reg .pred p;\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n"
+        "selp.u32 %0, 1, 0, p;\n}"
+        : "=r"(done)
+        : "r"(bar), "r"(c.phase)
+        : "memory");
+  }
+  c.phase ^= 1;
+}
+// index into dbuf of spectrum register e (stage-2 ownership)
+template <class P>
+__device__ __forceinline__ int data_index(const Cta<P>& c, int e) {
+  int dx, dy;
+  elem_offset<typename P::S2>(e, dx, dy);
+  return c.lbase + (pos_to_freq_y<P>(dy) * P::N + pos_to_freq_x<P>(dx));
+}
 
 // frame coordinates (y, x) of natural-ownership register e of column block cb
 template <class P>
@@ -166,11 +236,9 @@ __device__ __forceinline__ void gather_nat(float2 (&v)[P::E], const Cta<P>& c, i
 
 // ---------------------------------------------------------------- CTA-wide local transforms
 // forward: v (stage-0 ownership, natural order) -> v (stage-2 ownership, digit-reversed spectrum)
-// `pre()` runs between the second exchange and the last stage: the place to issue the global loads
-// (measured data) that the pointwise step needs, so that their latency hides behind stage 2.
-template <class P, class Pre>
+template <class P>
 __device__ __forceinline__ void fft_forward(float2 (&v)[P::E], float2* tile, const float2* tw,
-                                            int tid, Pre pre) {
+                                            int tid) {
   using TL = TwLayout<P>;
   int xf, yf;
   fixed_coords<typename P::S0, P::WBITS>(tid, xf, yf);
@@ -181,7 +249,6 @@ __device__ __forceinline__ void fft_forward(float2 (&v)[P::E], float2* tile, con
   stage_load<typename P::S1, P>(v, tile, xf, yf);
   stage_compute<typename P::S1, false>(v, xf, yf, tw + TL::X1, tw + TL::Y1);
   stage_store<typename P::S1, P>(v, tile, xf, yf);
-  pre();
   __syncthreads();
   fixed_coords<typename P::S2, P::WBITS>(tid, xf, yf);
   stage_load<typename P::S2, P>(v, tile, xf, yf);
@@ -255,29 +322,33 @@ __device__ __forceinline__ void frame_store_cross(const float2 (&v)[P::E], const
 // ---------------------------------------------------------------- pattern-level passes
 // gather(cb, v): fill v with the near plane of column block cb in natural ownership.
 // point(k1, v):  consume / modify the spectrum of sub-tile k1 (stage-2 ownership, spec_index).
+// after(k1):     runs once a block barrier has passed since point(k1): the place to re-arm the
+//                measured-data pipe (dp_issue) for the next tile.
 // near(cb, v):   consume the near plane of column block cb after the inverse transform.
 // Every pass ends with the shared tile free for reuse (trailing block barrier).
 
 // forward only: fwd operator, intensities, line-search costs.  `zero`: the pattern is skipped,
 // its far field is identically 0 and point() is evaluated on zeros without any transform.
-template <class P, class Gather, class Pre, class Point>
-__device__ __forceinline__ void spectrum_pass(const Cta<P>& c, bool zero, Gather gather, Pre pre,
-                                              Point point) {
+template <class P, class Gather, class Point, class After>
+__device__ __forceinline__ void spectrum_pass(Cta<P>& c, bool zero, Gather gather, Point point,
+                                              After after) {
   float2 v[P::E];
   if (zero) {
     for (int k1 = 0; k1 < P::RC; ++k1) {
 #pragma unroll
       for (int e = 0; e < P::E; ++e) v[e] = make_float2(0.f, 0.f);
-      pre(k1);
       point(k1, v);
+      __syncthreads();
+      after(k1);
     }
     return;
   }
   if (P::RC == 1) {
     gather(0, v);
-    fft_forward<P>(v, c.tile, c.tw, c.tid, [&]() { pre(0); });
+    fft_forward<P>(v, c.tile, c.tw, c.tid);
     point(0, v);
     __syncthreads();
+    after(0);
   } else {
     for (int cb = 0; cb < P::RC; ++cb) {
       gather(cb, v);
@@ -287,23 +358,25 @@ __device__ __forceinline__ void spectrum_pass(const Cta<P>& c, bool zero, Gather
     __syncthreads();
     for (int k1 = 0; k1 < P::RC; ++k1) {
       frame_load_s0<P>(v, c, k1);
-      fft_forward<P>(v, c.tile, c.tw, c.tid, [&]() { pre(k1); });
+      fft_forward<P>(v, c.tile, c.tw, c.tid);
       point(k1, v);
       __syncthreads();
+      after(k1);
     }
   }
 }
 
 // forward -> pointwise -> inverse with the spectrum kept in registers (the fused gradient)
-template <class P, class Gather, class Pre, class Point, class Near>
-__device__ __forceinline__ void fused_pass(const Cta<P>& c, Gather gather, Pre pre, Point point,
+template <class P, class Gather, class Point, class After, class Near>
+__device__ __forceinline__ void fused_pass(Cta<P>& c, Gather gather, Point point, After after,
                                            Near near) {
   float2 v[P::E];
   if (P::RC == 1) {
     gather(0, v);
-    fft_forward<P>(v, c.tile, c.tw, c.tid, [&]() { pre(0); });
+    fft_forward<P>(v, c.tile, c.tw, c.tid);
     point(0, v);
     fft_inverse<P>(v, c.tile, c.tw, c.tid);
+    after(0);
     near(0, v);
   } else {
     for (int cb = 0; cb < P::RC; ++cb) {
@@ -314,9 +387,10 @@ __device__ __forceinline__ void fused_pass(const Cta<P>& c, Gather gather, Pre p
     __syncthreads();
     for (int k1 = 0; k1 < P::RC; ++k1) {
       frame_load_s0<P>(v, c, k1);
-      fft_forward<P>(v, c.tile, c.tw, c.tid, [&]() { pre(k1); });
+      fft_forward<P>(v, c.tile, c.tw, c.tid);
       point(k1, v);
       fft_inverse<P>(v, c.tile, c.tw, c.tid);
+      after(k1);
       frame_store_s0<P>(v, c, k1);  // the positions this thread loaded: no hazard
       __syncthreads();              // tile reuse by the next sub-tile; frame complete after the last
     }
@@ -331,7 +405,7 @@ __device__ __forceinline__ void fused_pass(const Cta<P>& c, Gather gather, Pre p
 
 // inverse only: the API adjoints.  load(k1, v) fills the spectrum registers of sub-tile k1.
 template <class P, class Load, class Near>
-__device__ __forceinline__ void inverse_pass(const Cta<P>& c, Load load, Near near) {
+__device__ __forceinline__ void inverse_pass(Cta<P>& c, Load load, Near near) {
   float2 v[P::E];
   if (P::RC == 1) {
     load(0, v);

@@ -42,7 +42,8 @@ enum KernelId {
 
 struct PlanOps {
   int L, N, NT, RC;
-  size_t smem_bytes;       // dynamic shared memory of every kernel of the family
+  size_t smem_bytes;       // dynamic shared memory of the kernels that read measured data
+  size_t smem_bytes_nodata;  // ... of the others (no data tile: more of the SM's SRAM stays L1)
   size_t scratch_per_cta;  // float2
   int tw_total;            // float2
   void (*fill_tw)(float2*);

@@ -15,9 +15,15 @@ struct Smem {
   static constexpr int TILE = TileGeom<P>::WORDS;  // float2
   static constexpr int TW = TwLayout<P>::TOTAL;    // float2
   static constexpr int RED = (P::NT / 32) * 12;    // doubles: cross-warp reduction scratch
-  static constexpr int SLOTS = 9 * P::NT;          // doubles: per-thread running sums [k][tid]
-  static constexpr size_t BYTES =
-      (size_t)(TILE + TW) * sizeof(float2) + (size_t)(RED + SLOTS) * sizeof(double);
+  static constexpr int DBUF = P::NX * P::NY;       // floats: measured-data tile (TMA bulk copy)
+  static constexpr size_t OFF_TW = (size_t)TILE * sizeof(float2);
+  // [tile | twiddles | reduction scratch | mbarrier | data tile]: kernels that never read measured
+  // data are launched without the last part
+  static constexpr size_t OFF_RED = (OFF_TW + (size_t)TW * sizeof(float2) + 15) / 16 * 16;
+  static constexpr size_t OFF_BAR = OFF_RED + (size_t)RED * sizeof(double);
+  static constexpr size_t OFF_DBUF = (OFF_BAR + 16 + 127) / 128 * 128;
+  static constexpr size_t BYTES_NODATA = OFF_DBUF;
+  static constexpr size_t BYTES = OFF_DBUF + (size_t)DBUF * sizeof(float);
 };
 
 template <class P>
@@ -25,34 +31,43 @@ struct Scratch {  // per-CTA global scratch, in float2
   static constexpr size_t FRAME = P::RC > 1 ? (size_t)P::N * P::N : 0;
   static constexpr size_t STASH = (size_t)P::N * P::N;
   static constexpr size_t ACCP = (size_t)3 * P::N * P::N / 2;
-  static constexpr size_t TOTAL = FRAME + STASH + ACCP;
+  static constexpr size_t SLOTS = (size_t)9 * P::NT;  // doubles = float2-sized
+  static constexpr size_t TOTAL = FRAME + STASH + ACCP + SLOTS;
 };
 
 template <class P>
 __device__ __forceinline__ void cta_setup(Cta<P>& c, unsigned char* raw, const PassArgs& a) {
   c.tid = threadIdx.x;
   c.tile = reinterpret_cast<float2*>(raw);
-  float2* tw = c.tile + Smem<P>::TILE;
-  c.red = reinterpret_cast<double*>(tw + Smem<P>::TW);
-  c.slots = c.red + Smem<P>::RED + c.tid;  // this thread's running sums: slots[k * NT]
-#pragma unroll
-  for (int k = 0; k < 9; ++k) c.slots[k * P::NT] = 0.0;
+  float2* tw = reinterpret_cast<float2*>(raw + Smem<P>::OFF_TW);
+  c.dbuf = reinterpret_cast<float*>(raw + Smem<P>::OFF_DBUF);
+  c.red = reinterpret_cast<double*>(raw + Smem<P>::OFF_RED);
+  c.bar = reinterpret_cast<unsigned long long*>(raw + Smem<P>::OFF_BAR);
   for (int i = c.tid; i < Smem<P>::TW; i += P::NT) tw[i] = a.tw[i];
   c.tw = tw;
   float2* scr = a.scratch + (size_t)blockIdx.x * a.scratch_per_cta;
   c.frame = scr;
   c.stash = scr + Scratch<P>::FRAME;
   c.accp = reinterpret_cast<float*>(c.stash + Scratch<P>::STASH);
+  c.slots = reinterpret_cast<double*>(c.stash + Scratch<P>::STASH + Scratch<P>::ACCP) + c.tid;
+#pragma unroll
+  for (int k = 0; k < 9; ++k) c.slots[k * P::NT] = 0.0;
   fixed_coords<typename P::S0, P::WBITS>(c.tid, c.xf0, c.yf0);
   fixed_coords<typename P::S2, P::WBITS>(c.tid, c.xf2, c.yf2);
   c.sbase = spec_base<P>(c.xf2, c.yf2);
+  c.lbase = pos_to_freq_y<P>(c.yf2) * P::N + pos_to_freq_x<P>(c.xf2);
+  dp_init<P>(c);
   __syncthreads();
 }
 
 // Square roots / reciprocals through the SFU (MUFU.RSQ / MUFU.RCP, <= 2 ulp) instead of the IEEE
 // slow-path subroutines: a handful of instructions per pixel, and a relative error (2.4e-7) far
 // below the 1e-5 operator bar.  Arguments are clamped at 1e-35 so that exact zeros stay finite.
-__device__ __forceinline__ float frsq(float x) { return rsqrtf(fmaxf(x, 1e-35f)); }
+__device__ __forceinline__ float frsq(float x) {
+  float r;
+  asm("rsqrt.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(fmaxf(x, 1e-35f)));
+  return r;
+}
 __device__ __forceinline__ float fsqrt(float x) { return x * frsq(x); }  // 0 -> 0
 __device__ __forceinline__ float frcp(float x) {
   float r;
@@ -71,14 +86,6 @@ __device__ __forceinline__ float residual_factor(float d, float I, float fscale)
     return fmaf(-(fscale * d), frcp(I + 1e-32f), fscale);
 }
 
-// pull the next pattern's measured-data tile into L2 while this one is being transformed
-template <class P>
-__device__ __forceinline__ void prefetch_l2(const float* d, int tid) {
-  constexpr int LINES = P::N * P::N / 32;  // 128-byte lines
-  for (int i = tid; i < LINES; i += P::NT)
-    asm volatile("prefetch.global.L2 [%0];" ::"l"(d + (size_t)i * 32));
-}
-
 // minimisation functional per pixel (ptycho.py:308-314), x = intensity estimate, d = data
 template <int MODEL>
 __device__ __forceinline__ float minf_px(float x, float d, float sqd) {
@@ -91,12 +98,23 @@ __device__ __forceinline__ float minf_px(float x, float d, float sqd) {
   }
 }
 
+// re-arm the data pipe with the tile that follows (pat, k1) in this CTA's schedule
+template <class P>
+__device__ __forceinline__ void dp_next(const Cta<P>& c, const float* data, int pat, int k1, int npat) {
+  int nk = k1 + 1;
+  if (nk == P::RC) {
+    nk = 0;
+    pat += gridDim.x;
+  }
+  if (pat < npat) dp_issue<P>(c, data + (size_t)pat * P::N * P::N, nk);
+}
+
 // ------------------------------------------------------------------------------------------
 // API forward: g = FFT2(pad(kappa * prb * patch))                      (ptychofft.cu:60-73)
 // ------------------------------------------------------------------------------------------
 template <class P>
 __global__ void __launch_bounds__(P::NT) k_fwd(const PassArgs a) {
-  extern __shared__ __align__(16) unsigned char smem_raw[];
+  extern __shared__ __align__(128) unsigned char smem_raw[];
   Cta<P> c;
   cta_setup<P>(c, smem_raw, a);
   const Geo g = a.g;
@@ -109,11 +127,11 @@ __global__ void __launch_bounds__(P::NT) k_fwd(const PassArgs a) {
     const float2* prb_t = a.prb + (size_t)t * a.prb_ts;
     spectrum_pass<P>(
         c, p.skip, [&](int cb, float2(&v)[P::E]) { gather_nat<P>(v, c, cb, psi_t, prb_t, g, p); },
-        [](int) {},
         [&](int k1, float2(&v)[P::E]) {
 #pragma unroll
           for (int e = 0; e < P::E; ++e) out[spec_index<P>(c, k1, e)] = v[e];
-        });
+        },
+        [](int) {});
   }
 }
 
@@ -122,7 +140,7 @@ __global__ void __launch_bounds__(P::NT) k_fwd(const PassArgs a) {
 // through it.
 template <class P>
 __global__ void __launch_bounds__(P::NT) k_nearplane(const PassArgs a) {
-  extern __shared__ __align__(16) unsigned char smem_raw[];
+  extern __shared__ __align__(128) unsigned char smem_raw[];
   Cta<P> c;
   cta_setup<P>(c, smem_raw, a);
   const Geo g = a.g;
@@ -154,7 +172,7 @@ __global__ void __launch_bounds__(P::NT) k_nearplane(const PassArgs a) {
 // ------------------------------------------------------------------------------------------
 template <class P, int FLG>
 __global__ void __launch_bounds__(P::NT) k_adj(const PassArgs a) {
-  extern __shared__ __align__(16) unsigned char smem_raw[];
+  extern __shared__ __align__(128) unsigned char smem_raw[];
   Cta<P> c;
   cta_setup<P>(c, smem_raw, a);
   const Geo g = a.g;
@@ -193,55 +211,52 @@ __global__ void __launch_bounds__(P::NT) k_adj(const PassArgs a) {
 // CG pass A: I = sum_k |F_k|^2, reductions a = sum sqrt(I d), b = sum I, cost   (ptycho.py:330-343)
 // With several modes the running sum is parked in thread-private scratch between modes.
 // ------------------------------------------------------------------------------------------
-template <class P, int MODEL>
-__global__ void __launch_bounds__(P::NT) k_intensity(const PassArgs a) {
-  extern __shared__ __align__(16) unsigned char smem_raw[];
-  Cta<P> c;
-  cta_setup<P>(c, smem_raw, a);
+template <class P, int MODEL, bool MULTI>
+__device__ __forceinline__ void intensity_body(Cta<P>& c, const PassArgs& a) {
   const Geo g = a.g;
   const float iscale = a.sc ? a.sc[0] : 1.f;
   const int npat = g.T * g.S;
+  if ((int)blockIdx.x < npat) dp_issue<P>(c, a.data + (size_t)blockIdx.x * P::N * P::N, 0);
   for (int pat = blockIdx.x; pat < npat; pat += gridDim.x) {
     const int t = pat / g.S;
     const Pat p = make_pat(a.scan, pat, g);
     const float2* psi_t = a.psi + (size_t)t * g.nz * g.n;
-    const float* d = a.data + (size_t)pat * P::N * P::N;
     float* io = a.inten_out ? a.inten_out + (size_t)pat * P::N * P::N : nullptr;
-    if (pat + (int)gridDim.x < npat) prefetch_l2<P>(d + (size_t)gridDim.x * P::N * P::N, c.tid);
-    const int kfirst = p.skip ? a.nmodes - 1 : 0;  // a skipped pattern has I = 0: one zero pass
+    const int kfirst = (MULTI && !p.skip) ? 0 : a.nmodes - 1;  // a skipped pattern: one zero pass
     for (int k = kfirst; k < a.nmodes; ++k) {
       const float2* prb_k = a.prb + (size_t)t * a.prb_ts + (size_t)k * a.prb_ms;
-      const bool first = (k == kfirst), last = (k + 1 == a.nmodes);
-      float dreg[P::E];
+      const bool first = !MULTI || (k == kfirst), last = !MULTI || (k + 1 == a.nmodes);
       spectrum_pass<P>(
           c, p.skip, [&](int cb, float2(&v)[P::E]) { gather_nat<P>(v, c, cb, psi_t, prb_k, g, p); },
-          [&](int k1) {  // unconditional: a conditionally filled array would live in local memory
-#pragma unroll
-            for (int e = 0; e < P::E; ++e) dreg[e] = __ldg(d + spec_index<P>(c, k1, e));
-          },
           [&](int k1, float2(&v)[P::E]) {
             float* ia = c.accp + (size_t)k1 * P::E * P::NT + c.tid;
+            if (!last) {
+#pragma unroll
+              for (int e = 0; e < P::E; ++e) {
+                float I = v[e].x * v[e].x + v[e].y * v[e].y;
+                if (!first) I += ia[e * P::NT];
+                ia[e * P::NT] = I;
+              }
+              return;
+            }
             float sa = 0.f, sb = 0.f, scost = 0.f;  // fp32 over 32 pixels, double across tiles
+            dp_wait<P>(c);
 #pragma unroll
             for (int e = 0; e < P::E; ++e) {
               float I = v[e].x * v[e].x + v[e].y * v[e].y;
               if (!first) I += ia[e * P::NT];
-              if (!last) {
-                ia[e * P::NT] = I;
-              } else {
-                const int idx = spec_index<P>(c, k1, e);
-                const float dd = dreg[e];
-                sa += fsqrt(I * dd);
-                sb += I;
-                scost += minf_px<MODEL>(I * iscale, dd, fsqrt(dd));
-                if (io) io[idx] = I;
-              }
+              const float dd = c.dbuf[data_index<P>(c, e)];
+              sa += fsqrt(I * dd);
+              sb += I;
+              scost += minf_px<MODEL>(I * iscale, dd, fsqrt(dd));
+              if (io) io[spec_index<P>(c, k1, e)] = I;
             }
-            if (last) {
-              c.slots[0 * P::NT] += (double)sa;
-              c.slots[1 * P::NT] += (double)sb;
-              c.slots[2 * P::NT] += (double)scost;
-            }
+            c.slots[0 * P::NT] += (double)sa;
+            c.slots[1 * P::NT] += (double)sb;
+            c.slots[2 * P::NT] += (double)scost;
+          },
+          [&](int k1) {
+            if (last) dp_next<P>(c, a.data, pat, k1, npat);
           });
     }
   }
@@ -249,6 +264,16 @@ __global__ void __launch_bounds__(P::NT) k_intensity(const PassArgs a) {
 #pragma unroll
   for (int k = 0; k < 3; ++k) acc[k] = c.slots[k * P::NT];
   block_reduce_add<3, P::NT / 32>(acc, c.red, a.red, c.tid);
+}
+template <class P, int MODEL>
+__global__ void __launch_bounds__(P::NT) k_intensity(const PassArgs a) {
+  extern __shared__ __align__(128) unsigned char smem_raw[];
+  Cta<P> c;
+  cta_setup<P>(c, smem_raw, a);
+  if (a.nmodes == 1)
+    intensity_body<P, MODEL, false>(c, a);
+  else
+    intensity_body<P, MODEL, true>(c, a);
 }
 
 // ------------------------------------------------------------------------------------------
@@ -258,7 +283,7 @@ __global__ void __launch_bounds__(P::NT) k_intensity(const PassArgs a) {
 // ------------------------------------------------------------------------------------------
 template <class P, int MODEL, int WHAT>
 __global__ void __launch_bounds__(P::NT) k_grad(const PassArgs a) {
-  extern __shared__ __align__(16) unsigned char smem_raw[];
+  extern __shared__ __align__(128) unsigned char smem_raw[];
   Cta<P> c;
   cta_setup<P>(c, smem_raw, a);
   const Geo g = a.g;
@@ -266,6 +291,7 @@ __global__ void __launch_bounds__(P::NT) k_grad(const PassArgs a) {
   if (WHAT == 1) pacc_zero<P>(c);
   int t_cur = -1;
   const int npat = g.T * g.S;
+  if ((int)blockIdx.x < npat) dp_issue<P>(c, a.data + (size_t)blockIdx.x * P::N * P::N, 0);
   for (int pat = blockIdx.x; pat < npat; pat += gridDim.x) {
     const int t = pat / g.S;
     if (WHAT == 1 && t != t_cur) {
@@ -273,31 +299,33 @@ __global__ void __launch_bounds__(P::NT) k_grad(const PassArgs a) {
       t_cur = t;
     }
     const Pat p = make_pat(a.scan, pat, g);
-    if (p.skip) continue;  // F = 0 -> residual 0 -> no contribution
+    if (p.skip) {  // F = 0 -> residual 0 -> no contribution; drain the data pipe all the same
+      for (int k1 = 0; k1 < P::RC; ++k1) {
+        dp_wait<P>(c);
+        __syncthreads();
+        dp_next<P>(c, a.data, pat, k1, npat);
+      }
+      continue;
+    }
     const float2* psi_t = a.psi + (size_t)t * g.nz * g.n;
     const float2* prb_t = a.prb + (size_t)t * a.prb_ts;
     float2* grad_t = a.grad + (size_t)t * g.nz * g.n;
-    const float* d = a.data + (size_t)pat * P::N * P::N;
     const float* ii = a.inten_in ? a.inten_in + (size_t)pat * P::N * P::N : nullptr;
-    if (pat + (int)gridDim.x < npat) prefetch_l2<P>(d + (size_t)gridDim.x * P::N * P::N, c.tid);
-    float dreg[P::E];
     fused_pass<P>(
         c, [&](int cb, float2(&v)[P::E]) { gather_nat<P>(v, c, cb, psi_t, prb_t, g, p); },
-        [&](int k1) {
-#pragma unroll
-          for (int e = 0; e < P::E; ++e) dreg[e] = __ldg(d + spec_index<P>(c, k1, e));
-        },
         [&](int k1, float2(&v)[P::E]) {
+          dp_wait<P>(c);
 #pragma unroll
           for (int e = 0; e < P::E; ++e) {
-            const int idx = spec_index<P>(c, k1, e);
-            const float dd = dreg[e];
-            const float I = ii ? __ldg(ii + idx) * iscale : (v[e].x * v[e].x + v[e].y * v[e].y);
+            const float dd = c.dbuf[data_index<P>(c, e)];
+            const float I = ii ? __ldg(ii + spec_index<P>(c, k1, e)) * iscale
+                               : (v[e].x * v[e].x + v[e].y * v[e].y);
             const float f = residual_factor<MODEL>(dd, I, fscale);
             v[e].x *= f;
             v[e].y *= f;
           }
         },
+        [&](int k1) { dp_next<P>(c, a.data, pat, k1, npat); },
         [&](int cb, float2(&v)[P::E]) {
           if (WHAT == 0)
             scatter_block<P>(v, c, cb, prb_t, gscale, grad_t, g, p);
@@ -309,53 +337,48 @@ __global__ void __launch_bounds__(P::NT) k_grad(const PassArgs a) {
 }
 
 // ------------------------------------------------------------------------------------------
-// CG pass C/E: line-search costs for up to 8 step candidates at once
+// CG pass C/E: line-search costs for 4 step candidates 2^-c0 .. 2^-(c0+3) at once
 //   ptycho.py:383-393 (object), 451-461 (probe), 253-281 (line_search_sqr)
 // The first far field of a pair is parked in thread-private scratch while the second is transformed.
 // ------------------------------------------------------------------------------------------
 template <class P, int MODEL>
 __global__ void __launch_bounds__(P::NT) k_linesearch(const PassArgs a) {
-  extern __shared__ __align__(16) unsigned char smem_raw[];
+  extern __shared__ __align__(128) unsigned char smem_raw[];
   Cta<P> c;
   cta_setup<P>(c, smem_raw, a);
   const Geo g = a.g;
   constexpr size_t NN = (size_t)P::N * P::N;
   const bool multi = a.npairs > 1;
   const int npat = g.T * g.S;
+  const float gam0 = exp2f(-(float)a.c0);
+  if ((int)blockIdx.x < npat) dp_issue<P>(c, a.data + (size_t)blockIdx.x * NN, 0);
   for (int pat = blockIdx.x; pat < npat; pat += gridDim.x) {
     const int t = pat / g.S;
     const Pat p = make_pat(a.scan, pat, g);
-    const float* d = a.data + (size_t)pat * NN;
     const float* p1in = a.inten_in ? a.inten_in + (size_t)pat * NN : nullptr;
     const float2* psi_a = a.psi + (size_t)t * g.nz * g.n;
     const float2* psi_b = a.psi_b + (size_t)t * g.nz * g.n;
-    float dreg[P::E];
-    if (pat + (int)gridDim.x < npat) prefetch_l2<P>(d + (size_t)gridDim.x * NN, c.tid);
     for (int j = 0; j < a.npairs; ++j) {
       const float2* prb_a = a.prb + (size_t)t * a.prb_ts + (size_t)j * a.prb_ms;
       const float2* prb_b = a.prb_b + (size_t)t * a.prb_b_ts + (size_t)j * a.prb_b_ms;
       const bool first = (j == 0), last = (j + 1 == a.npairs);
       spectrum_pass<P>(
           c, p.skip, [&](int cb, float2(&v)[P::E]) { gather_nat<P>(v, c, cb, psi_a, prb_a, g, p); },
-          [](int) {},
           [&](int k1, float2(&v)[P::E]) {
             float2* st = c.stash + (size_t)k1 * P::E * P::NT + c.tid;
 #pragma unroll
             for (int e = 0; e < P::E; ++e) st[e * P::NT] = v[e];
-          });
+          },
+          [](int) {});
       spectrum_pass<P>(
           c, p.skip, [&](int cb, float2(&v)[P::E]) { gather_nat<P>(v, c, cb, psi_b, prb_b, g, p); },
-          [&](int k1) {  // unconditional: a conditionally filled array would live in local memory
-#pragma unroll
-            for (int e = 0; e < P::E; ++e) dreg[e] = __ldg(d + spec_index<P>(c, k1, e));
-          },
           [&](int k1, float2(&v)[P::E]) {
             const float2* st = c.stash + (size_t)k1 * P::E * P::NT + c.tid;
             float* ap = c.accp + (size_t)k1 * P::E * P::NT + c.tid;
-            float cost[9];  // fp32 over 32 pixels, double across tiles (per-thread smem slots)
+            float cost[5];  // fp32 over 32 pixels, double across tiles
 #pragma unroll
-            for (int q = 0; q < 9; ++q) cost[q] = 0.f;
-            const float gam0 = exp2f(-(float)a.c0);
+            for (int q = 0; q < 5; ++q) cost[q] = 0.f;
+            if (last) dp_wait<P>(c);
 #pragma unroll
             for (int e = 0; e < P::E; ++e) {
               const float2 t1 = st[e * P::NT];
@@ -376,30 +399,32 @@ __global__ void __launch_bounds__(P::NT) k_linesearch(const PassArgs a) {
                 }
               }
               if (last) {
-                const int idx = spec_index<P>(c, k1, e);
-                const float dd = dreg[e];
+                const float dd = c.dbuf[data_index<P>(c, e)];
                 const float sqd = fsqrt(dd);
-                if (p1in) q1 = __ldg(p1in + idx);
+                if (p1in) q1 = __ldg(p1in + spec_index<P>(c, k1, e));
                 cost[0] += minf_px<MODEL>(q1, dd, sqd);
                 float gam = gam0;
 #pragma unroll
-                for (int q = 0; q < 8; ++q) {
-                  if (q < a.ncand) cost[1 + q] += minf_px<MODEL>(q1 + gam * gam * q2 + gam * q3, dd, sqd);
+                for (int q = 0; q < 4; ++q) {
+                  cost[1 + q] += minf_px<MODEL>(q1 + gam * gam * q2 + gam * q3, dd, sqd);
                   gam *= 0.5f;
                 }
               }
             }
             if (last) {
 #pragma unroll
-              for (int q = 0; q < 9; ++q) c.slots[q * P::NT] += (double)cost[q];
+              for (int q = 0; q < 5; ++q) c.slots[q * P::NT] += (double)cost[q];
             }
+          },
+          [&](int k1) {
+            if (last) dp_next<P>(c, a.data, pat, k1, npat);
           });
     }
   }
-  double acc[9];
+  double acc[5];
 #pragma unroll
-  for (int q = 0; q < 9; ++q) acc[q] = c.slots[q * P::NT];
-  block_reduce_add<9, P::NT / 32>(acc, c.red, a.red, c.tid);
+  for (int q = 0; q < 5; ++q) acc[q] = c.slots[q * P::NT];
+  block_reduce_add<5, P::NT / 32>(acc, c.red, a.red, c.tid);
 }
 
 // ------------------------------------------------------------------------------------------
@@ -420,6 +445,7 @@ const PlanOps* make_ops() {
     ops.NT = P::NT;
     ops.RC = P::RC;
     ops.smem_bytes = Smem<P>::BYTES;
+    ops.smem_bytes_nodata = Smem<P>::BYTES_NODATA;
     ops.scratch_per_cta = Scratch<P>::TOTAL;
     ops.tw_total = TwLayout<P>::TOTAL;
     ops.fill_tw = fill_tw_host<P>;

@@ -230,6 +230,16 @@ class CGPtychoSolver(PtychoCuFFT):
     #: diagnostics hook used by the parity tests: a list of raw line-search results, consumed in call
     #: order, that override the solver's own decisions (the costs are still evaluated and logged)
     _forced_steps = None
+    #: optional libtike.cufft.dist.ScalarComm: when set, the CG scalars (and, in shared-probe mode,
+    #: the probe gradient) are all-reduced over its process group, so that ranks holding different
+    #: angles behave like ONE reference run over all of them
+    comm = None
+
+    def _sum(self, t):
+        return self.comm.sum_(t) if self.comm is not None else t
+
+    def _max(self, t):
+        return self.comm.max_(t) if self.comm is not None else t
 
     @staticmethod
     def line_search_sqr(f, p1, p2, p3, step_length=1, step_shrink=0.5):
@@ -255,7 +265,7 @@ class CGPtychoSolver(PtychoCuFFT):
                                    _ptr(data), _ptr(inten) if inten is not None else None,
                                    _ptr(sc) if sc is not None else None, model, _ptr(red),
                                    current_stream()))
-        return red
+        return self._sum(red)
 
     def _grad(self, what, psi, scan, probe, mode, data, inten, fscale, iscale, gscale, model, out,
               out_stride=0):
@@ -276,7 +286,7 @@ class CGPtychoSolver(PtychoCuFFT):
                                         _ptr(prb_b), nm_b, m_b, npairs, _ptr(scan), _ptr(data),
                                         _ptr(p1) if p1 is not None else None, model, c0, K,
                                         _ptr(cost), current_stream()))
-            c = cost.cpu().numpy()
+            c = self._sum(cost).cpu().numpy()
             self.ls_log.append((c0, c[:1 + K].copy()))
             if forced is not None and (forced == 0 or forced >= 2.0 ** -(c0 + K - 1)):
                 return forced
@@ -295,6 +305,7 @@ class CGPtychoSolver(PtychoCuFFT):
         if not first:
             check(lib.ptx_vec_dai_yuan_reduce(_ptr(grad), _ptr(grad0), _ptr(d), n, _ptr(red),
                                               current_stream()))
+            self._sum(red)
         check(lib.ptx_vec_dai_yuan_update(_ptr(grad), _ptr(grad0), _ptr(d), n, _ptr(red),
                                           1 if first else 0, current_stream()))
 
@@ -309,7 +320,7 @@ class CGPtychoSolver(PtychoCuFFT):
         else:  # probe[:, k] with ptheta > 1: one launch per angle, same accumulator
             for t in range(x.shape[0]):
                 check(lib.ptx_vec_absmax(_ptr(x[t]), x[t].numel(), _ptr(out), current_stream()))
-        return out
+        return self._max(out)
 
     # ------------------------------------------------------------------ fused gradient, host arrays
     def grad_ptycho_batch(self, data, psi, scan, probe, model="gaussian"):
@@ -415,7 +426,7 @@ class CGPtychoSolver(PtychoCuFFT):
         dev = psi.device
         multi = M > 1
         inten = torch.empty_like(data) if multi else None
-        sum_data = float(data.sum(dtype=torch.float64)) if mdl == 0 else 0.0
+        sum_data = float(self._sum(data.sum(dtype=torch.float64).reshape(1))) if mdl == 0 else 0.0
 
         gradpsi = torch.zeros_like(psi)
         gradpsi0 = torch.zeros_like(psi)
@@ -473,6 +484,8 @@ class CGPtychoSolver(PtychoCuFFT):
                     gradprb[m].zero_()
                     self._grad(1, psi, scan, probe, m, data, inten, 1.0, 1.0, gscale, mdl,
                                gradprb[m], P * P)
+                    if self.comm is not None:
+                        self.comm.probe_grad_(gradprb[m])
                     # Dai-Yuan direction (ptycho.py:442-450)
                     self._dai_yuan(gradprb[m], gradprb0[m], dprb[m], i == 0)
                     # line search (ptycho.py:451-461)
