@@ -8,6 +8,7 @@
 // There is no CPU or library fallback: unsupported sizes return PTX_EUNSUPPORTED.
 #include <cuda_runtime.h>
 #include <stdarg.h>
+#include <stdint.h>
 #include <stdio.h>
 #include <stdlib.h>
 #include <string.h>
@@ -173,11 +174,55 @@ static bool debug_sync() {
   return on;
 }
 
+// Tensor map of an object array [T, nz, n] complex64 (8-byte elements) with the plan's patch box.
+// TMA needs a 16-byte aligned base and row pitch: odd object widths fall back to plain loads.
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*,
+                                  CUtensorMapInterleave, CUtensorMapSwizzle, CUtensorMapL2promotion,
+                                  CUtensorMapFloatOOBfill);
+static EncodeTiledFn encode_fn() {
+  static EncodeTiledFn fn = []() -> EncodeTiledFn {
+    void* f = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &f, cudaEnableDefault, &q) != cudaSuccess ||
+        q != cudaDriverEntryPointSuccess)
+      return nullptr;
+    return (EncodeTiledFn)f;
+  }();
+  return fn;
+}
+static bool make_object_map(const ptx_plan* p, const void* psi, CUtensorMap* tm) {
+  const PlanOps* ops = p->ops;
+  static const bool off = getenv("PTX_NO_TMA_GATHER") != nullptr;
+  if (off || !ops->patch_w || !psi || ((uintptr_t)psi & 15) || (p->n & 1) || !encode_fn()) return false;
+  const cuuint64_t dims[3] = {p->n, p->nz, p->ptheta};
+  const cuuint64_t strides[2] = {p->n * 8, p->n * p->nz * 8};
+  const cuuint32_t box[3] = {(cuuint32_t)ops->patch_w, (cuuint32_t)ops->patch_h, 1};
+  const cuuint32_t estr[3] = {1, 1, 1};
+  return encode_fn()(tm, CU_TENSOR_MAP_DATA_TYPE_UINT64, 3, const_cast<void*>(psi), dims, strides, box,
+                     estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE,
+                     CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
+}
+
 static int launch(ptx_plan* p, int kid, PassArgs& a, cudaStream_t st) {
   const PlanOps* ops = p->ops;
   const int npat = a.g.T * a.g.S;
   const int grid = npat < p->grid ? npat : p->grid;
-  void* params[] = {&a};
+  alignas(64) CUtensorMap tm_a, tm_b;
+  memset(&tm_a, 0, sizeof(tm_a));
+  memset(&tm_b, 0, sizeof(tm_b));
+  a.use_tma = 0;
+  // TMA patch gather pays where measured (profiles/): every forward-only pass of the multi-block
+  // plans (N = 256) and the line search; elsewhere the strided read-only loads are as fast
+  static const bool force = getenv("PTX_TMA_GATHER_ALL") != nullptr;
+  const bool ls = (kid == K_LS_GAUSS || kid == K_LS_POIS);
+  const bool fwd_only = ls || kid == K_FWD || kid == K_INT_GAUSS || kid == K_INT_POIS;
+  const bool want = force || ls || (ops->RC > 1 && fwd_only);
+  if (want && kid != K_NEAR && kid != K_ADJ_OBJ && kid != K_ADJ_PRB && a.psi) {
+    const bool two = (kid == K_LS_GAUSS || kid == K_LS_POIS);
+    if (make_object_map(p, a.psi, &tm_a) && (!two || make_object_map(p, a.psi_b, &tm_b))) a.use_tma = 1;
+  }
+  void* params[] = {&a, &tm_a, &tm_b};
   const bool nodata = kid == K_FWD || kid == K_NEAR || kid == K_ADJ_OBJ || kid == K_ADJ_PRB;
   cudaError_t e = cudaLaunchKernel(ops->kernels[kid], dim3(grid), dim3(ops->NT), params,
                                    nodata ? ops->smem_bytes_nodata : ops->smem_bytes, st);

@@ -91,8 +91,10 @@ struct Cta {
   const float2* tw;    // shared twiddle tables
   double* red;         // shared cross-warp reduction scratch
   float* dbuf;         // shared: the measured-data tile of the current (sub-)spectrum, NY x NX f32
-  unsigned long long* bar;  // shared mbarrier: completion of the bulk copy into dbuf
-  unsigned phase;      // parity of the next completion to wait for
+  unsigned long long* bar;  // shared mbarriers: [0] bulk copy into dbuf, [1] object-patch tensor copy
+  unsigned phase;      // parity of the next dbuf completion to wait for
+  unsigned phase2;     // ... of the next patch completion
+  int pshift;          // 0/1: column offset of the patch inside its (even-aligned) TMA box
   double* slots;       // global thread-private running sums: slots[k * NT], k < 9
   float2* frame;       // global scratch frame [RC][NY][NX] (RC > 1 only)
   float2* stash;       // global thread-private scratch, N*N complex: [(k*E + e)*NT + tid]
@@ -116,9 +118,23 @@ template <class P>
 __device__ __forceinline__ void dp_init(Cta<P>& c) {
   if (c.tid == 0) {
     asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(smem_u32(c.bar)));
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(smem_u32(c.bar + 1)));
     asm volatile("fence.mbarrier_init.release.cluster;");
   }
   c.phase = 0;
+  c.phase2 = 0;
+}
+__device__ __forceinline__ void mbar_wait(unsigned bar, unsigned phase) {
+  unsigned done = 0;
+  while (!done) {
+    asm volatile(
+        "{\n.reg .pred p;\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n"
+        "selp.u32 %0, 1, 0, p;\n}"
+        : "=r"(done)
+        : "r"(bar), "r"(phase)
+        : "memory");
+  }
 }
 template <class P>
 __device__ __forceinline__ void dp_issue(const Cta<P>& c, const float* d_pat, int k1) {
@@ -147,17 +163,7 @@ __device__ __forceinline__ void dp_issue(const Cta<P>& c, const float* d_pat, in
 }
 template <class P>
 __device__ __forceinline__ void dp_wait(Cta<P>& c) {
-  const unsigned bar = smem_u32(c.bar);
-  unsigned done = 0;
-  while (!done) {
-    asm volatile(
-        "{\n.reg .pred p;\n"
-        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n"
-        "selp.u32 %0, 1, 0, p;\n}"
-        : "=r"(done)
-        : "r"(bar), "r"(c.phase)
-        : "memory");
-  }
+  mbar_wait(smem_u32(c.bar), c.phase);
   c.phase ^= 1;
 }
 // index into dbuf of spectrum register e (stage-2 ownership)
@@ -232,6 +238,86 @@ __device__ __forceinline__ void gather_nat(float2 (&v)[P::E], const Cta<P>& c, i
   } else {
     gather_impl<P, false, false>(v, c, cb, psi_t, prb, g, p);
   }
+}
+
+// ---------------------------------------------------------------- object patch by TMA tensor copy
+// The (N+1) x (CW+1) object window under column block cb is pulled into the (free) shared tile by
+// cp.async.bulk.tensor (UTMALDG): one instruction instead of 4 x 32 strided global loads per thread,
+// every object pixel crosses L2 -> SM once, and pixels outside the object arrive as zeros (the zero
+// extension of patch_at<false>).  The box starts at frame pixel (0, cb*CW), i.e. at
+// object pixel (R - o, C - o + cb*CW), so frame pixel (y, x) has its taps at [y][x - cb*CW] + {0,1}.
+template <class P>
+struct Patch {
+  static constexpr bool TMA = P::N <= 256;
+  // box width: CW + 1 columns are needed; TMA wants the box to START on a 16-byte boundary of the
+  // global row (measured: an odd complex64 column coordinate raises "illegal instruction"), so the
+  // box starts at the even column at or left of the patch and is one column wider; even width.
+  static constexpr int W = Cross<P>::CW + 4;
+  static constexpr int H = P::N >= 256 ? 129 : P::N + 1;        // box height (<= 256)
+  static constexpr int NLOAD = P::N >= 256 ? P::N / 128 : 1;    // boxes stacked every 128 rows
+  static constexpr unsigned BYTES = (unsigned)NLOAD * H * W * 8;
+  static constexpr int WORDS = ((NLOAD - 1) * 128 + H) * W;     // float2, lands in the tile region
+};
+template <class P>
+__device__ __forceinline__ void patch_issue(Cta<P>& c, const CUtensorMap* tm, const Geo& g,
+                                            const Pat& p, int t, int cb) {
+  const int cx0 = p.C - g.o + cb * Cross<P>::CW;
+  c.pshift = cx0 & 1;  // column of frame pixel x inside the landed box: (x - cb*CW) + pshift
+  if (c.tid != 0) return;
+  const unsigned bar = smem_u32(c.bar + 1);
+  asm volatile("fence.proxy.async.shared::cta;");
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(Patch<P>::BYTES));
+  const int cx = cx0 - (cx0 & 1), cy = p.R - g.o;
+#pragma unroll
+  for (int j = 0; j < Patch<P>::NLOAD; ++j)
+    asm volatile(
+        "cp.async.bulk.tensor.3d.shared::cluster.global.tile.mbarrier::complete_tx::bytes "
+        "[%0], [%1, {%2, %3, %4}], [%5];" ::"r"(smem_u32(c.tile + j * 128 * Patch<P>::W)),
+        "l"(tm), "r"(cx), "r"(cy + 128 * j), "r"(t), "r"(bar)
+        : "memory");
+}
+// near plane of block cb from the landed patch; ends with a block barrier (the tile is about to be
+// overwritten by the transform / the next patch)
+template <class P, bool FULL>
+__device__ __forceinline__ void gather_tma_impl(float2 (&v)[P::E], Cta<P>& c, int cb, int shift,
+                                                const float2* __restrict__ prb, const Geo& g,
+                                                const Pat& p) {
+  constexpr int W = Patch<P>::W;
+  // probe values first: their L2 latency overlaps the wait for the tensor copy
+#pragma unroll
+  for (int e = 0; e < P::E; ++e) {
+    int y, x;
+    nat_coord<P>(c, cb, e, y, x);
+    const int iy = FULL ? y : y - g.o, ix = FULL ? x : x - g.o;
+    v[e] = make_float2(0.f, 0.f);
+    if (FULL || ((unsigned)iy < (unsigned)g.P && (unsigned)ix < (unsigned)g.P))
+      v[e] = __ldg(prb + iy * g.P + ix);
+  }
+  mbar_wait(smem_u32(c.bar + 1), c.phase2);
+  c.phase2 ^= 1;
+  const float k00 = g.kappa * p.w00, k01 = g.kappa * p.w01, k10 = g.kappa * p.w10, k11 = g.kappa * p.w11;
+#pragma unroll
+  for (int e = 0; e < P::E; ++e) {
+    int y, x;
+    nat_coord<P>(c, cb, e, y, x);
+    const float2* q = c.tile + y * W + (x - cb * Cross<P>::CW) + shift;
+    const float2 f00 = q[0], f01 = q[1], f10 = q[W], f11 = q[W + 1];
+    float2 t;
+    t.x = f00.x * k00 + f01.x * k01 + f10.x * k10 + f11.x * k11;
+    t.y = f00.y * k00 + f01.y * k01 + f10.y * k10 + f11.y * k11;
+    const float2 pr = v[e];
+    v[e] = make_float2(pr.x * t.x - pr.y * t.y, pr.x * t.y + pr.y * t.x);
+  }
+  __syncthreads();
+}
+template <class P>
+__device__ __forceinline__ void gather_tma(float2 (&v)[P::E], Cta<P>& c, int cb, int shift,
+                                           const float2* __restrict__ prb, const Geo& g,
+                                           const Pat& p) {
+  if (g.P == P::N)
+    gather_tma_impl<P, true>(v, c, cb, shift, prb, g, p);
+  else
+    gather_tma_impl<P, false>(v, c, cb, shift, prb, g, p);
 }
 
 // ---------------------------------------------------------------- CTA-wide local transforms

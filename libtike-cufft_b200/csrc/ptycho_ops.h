@@ -2,6 +2,7 @@
 // (plan_l6.cu ... plan_l9.cu, one translation unit each so that they compile in parallel).
 #pragma once
 
+#include <cuda.h>  // CUtensorMap (type only: the driver entry point is looked up at run time)
 #include <cuda_runtime.h>
 #include <stddef.h>
 
@@ -32,6 +33,7 @@ struct PassArgs {
   const float* sc;  // device scalars
   double* red;
   int nmodes, npairs, c0, ncand;
+  int use_tma;  // object patches arrive by TMA tensor copies (tensor maps are valid)
 };
 
 enum KernelId {
@@ -47,6 +49,7 @@ struct PlanOps {
   size_t scratch_per_cta;  // float2
   int tw_total;            // float2
   void (*fill_tw)(float2*);
+  int patch_w, patch_h;    // TMA box of the object patch in complex elements (0: no TMA gather)
   const void* kernels[K_COUNT];
   const char* names[K_COUNT];
 };

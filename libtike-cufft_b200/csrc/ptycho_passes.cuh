@@ -12,7 +12,10 @@ namespace ptx {
 
 template <class P>
 struct Smem {
-  static constexpr int TILE = TileGeom<P>::WORDS;  // float2
+  // float2: the FFT tile; the TMA-landed object patch reuses the region and may be a bit larger
+  static constexpr int TILE = (Patch<P>::TMA && Patch<P>::WORDS > TileGeom<P>::WORDS)
+                                  ? ((Patch<P>::WORDS + 15) / 16 * 16)
+                                  : TileGeom<P>::WORDS;
   static constexpr int TW = TwLayout<P>::TOTAL;    // float2
   static constexpr int RED = (P::NT / 32) * 12;    // doubles: cross-warp reduction scratch
   static constexpr int DBUF = P::NX * P::NY;       // floats: measured-data tile (TMA bulk copy)
@@ -98,6 +101,29 @@ __device__ __forceinline__ float minf_px(float x, float d, float sqd) {
   }
 }
 
+// near plane of column block cb: object patch by TMA tensor copy when the tensor map is usable,
+// strided read-only loads otherwise (odd object width, unaligned base, 512^2 detectors).
+// With several column blocks (N > 128) the copy of block cb+1 is issued as soon as block cb's taps
+// have been read, so that it overlaps the cross butterfly and the frame stores of block cb.
+template <class P>
+__device__ __forceinline__ void gather_any(float2 (&v)[P::E], Cta<P>& c, int cb, bool use_tma,
+                                           const CUtensorMap* tm, int t,
+                                           const float2* __restrict__ psi_t,
+                                           const float2* __restrict__ prb, const Geo& g,
+                                           const Pat& p) {
+  if (Patch<P>::TMA && use_tma) {
+    if (cb == 0) {
+      __syncthreads();  // every thread is done with the tile (e.g. the last inverse stage's loads)
+      patch_issue<P>(c, tm, g, p, t, 0);
+    }
+    const int shift = c.pshift;
+    gather_tma<P>(v, c, cb, shift, prb, g, p);  // ends with a block barrier: the tile is free again
+    if (cb + 1 < P::RC) patch_issue<P>(c, tm, g, p, t, cb + 1);
+  } else {
+    gather_nat<P>(v, c, cb, psi_t, prb, g, p);
+  }
+}
+
 // re-arm the data pipe with the tile that follows (pat, k1) in this CTA's schedule
 template <class P>
 __device__ __forceinline__ void dp_next(const Cta<P>& c, const float* data, int pat, int k1, int npat) {
@@ -113,7 +139,8 @@ __device__ __forceinline__ void dp_next(const Cta<P>& c, const float* data, int 
 // API forward: g = FFT2(pad(kappa * prb * patch))                      (ptychofft.cu:60-73)
 // ------------------------------------------------------------------------------------------
 template <class P>
-__global__ void __launch_bounds__(P::NT) k_fwd(const PassArgs a) {
+__global__ void __launch_bounds__(P::NT) k_fwd(const PassArgs a, const __grid_constant__ CUtensorMap tm_a,
+                                               const __grid_constant__ CUtensorMap tm_b) {
   extern __shared__ __align__(128) unsigned char smem_raw[];
   Cta<P> c;
   cta_setup<P>(c, smem_raw, a);
@@ -126,7 +153,9 @@ __global__ void __launch_bounds__(P::NT) k_fwd(const PassArgs a) {
     const float2* psi_t = a.psi + (size_t)t * g.nz * g.n;
     const float2* prb_t = a.prb + (size_t)t * a.prb_ts;
     spectrum_pass<P>(
-        c, p.skip, [&](int cb, float2(&v)[P::E]) { gather_nat<P>(v, c, cb, psi_t, prb_t, g, p); },
+        c, p.skip, [&](int cb, float2(&v)[P::E]) {
+          gather_any<P>(v, c, cb, a.use_tma, &tm_a, t, psi_t, prb_t, g, p);
+        },
         [&](int k1, float2(&v)[P::E]) {
 #pragma unroll
           for (int e = 0; e < P::E; ++e) out[spec_index<P>(c, k1, e)] = v[e];
@@ -139,7 +168,9 @@ __global__ void __launch_bounds__(P::NT) k_fwd(const PassArgs a) {
 // order.  Integer work of the path (patch origin, window offset, skip rule) is checked bit-exactly
 // through it.
 template <class P>
-__global__ void __launch_bounds__(P::NT) k_nearplane(const PassArgs a) {
+__global__ void __launch_bounds__(P::NT) k_nearplane(const PassArgs a,
+                                                     const __grid_constant__ CUtensorMap tm_a,
+                                                     const __grid_constant__ CUtensorMap tm_b) {
   extern __shared__ __align__(128) unsigned char smem_raw[];
   Cta<P> c;
   cta_setup<P>(c, smem_raw, a);
@@ -171,7 +202,8 @@ __global__ void __launch_bounds__(P::NT) k_nearplane(const PassArgs a) {
 // API adjoints: inverse FFT + object scatter (FLG 0) or probe reduction (FLG 1)  (ptychofft.cu:76-88)
 // ------------------------------------------------------------------------------------------
 template <class P, int FLG>
-__global__ void __launch_bounds__(P::NT) k_adj(const PassArgs a) {
+__global__ void __launch_bounds__(P::NT) k_adj(const PassArgs a, const __grid_constant__ CUtensorMap tm_a,
+                                               const __grid_constant__ CUtensorMap tm_b) {
   extern __shared__ __align__(128) unsigned char smem_raw[];
   Cta<P> c;
   cta_setup<P>(c, smem_raw, a);
@@ -212,7 +244,7 @@ __global__ void __launch_bounds__(P::NT) k_adj(const PassArgs a) {
 // With several modes the running sum is parked in thread-private scratch between modes.
 // ------------------------------------------------------------------------------------------
 template <class P, int MODEL, bool MULTI>
-__device__ __forceinline__ void intensity_body(Cta<P>& c, const PassArgs& a) {
+__device__ __forceinline__ void intensity_body(Cta<P>& c, const PassArgs& a, const CUtensorMap* tm) {
   const Geo g = a.g;
   const float iscale = a.sc ? a.sc[0] : 1.f;
   const int npat = g.T * g.S;
@@ -227,7 +259,9 @@ __device__ __forceinline__ void intensity_body(Cta<P>& c, const PassArgs& a) {
       const float2* prb_k = a.prb + (size_t)t * a.prb_ts + (size_t)k * a.prb_ms;
       const bool first = !MULTI || (k == kfirst), last = !MULTI || (k + 1 == a.nmodes);
       spectrum_pass<P>(
-          c, p.skip, [&](int cb, float2(&v)[P::E]) { gather_nat<P>(v, c, cb, psi_t, prb_k, g, p); },
+          c, p.skip, [&](int cb, float2(&v)[P::E]) {
+            gather_any<P>(v, c, cb, a.use_tma, tm, t, psi_t, prb_k, g, p);
+          },
           [&](int k1, float2(&v)[P::E]) {
             float* ia = c.accp + (size_t)k1 * P::E * P::NT + c.tid;
             if (!last) {
@@ -266,14 +300,16 @@ __device__ __forceinline__ void intensity_body(Cta<P>& c, const PassArgs& a) {
   block_reduce_add<3, P::NT / 32>(acc, c.red, a.red, c.tid);
 }
 template <class P, int MODEL>
-__global__ void __launch_bounds__(P::NT) k_intensity(const PassArgs a) {
+__global__ void __launch_bounds__(P::NT) k_intensity(const PassArgs a,
+                                                     const __grid_constant__ CUtensorMap tm_a,
+                                                     const __grid_constant__ CUtensorMap tm_b) {
   extern __shared__ __align__(128) unsigned char smem_raw[];
   Cta<P> c;
   cta_setup<P>(c, smem_raw, a);
   if (a.nmodes == 1)
-    intensity_body<P, MODEL, false>(c, a);
+    intensity_body<P, MODEL, false>(c, a, &tm_a);
   else
-    intensity_body<P, MODEL, true>(c, a);
+    intensity_body<P, MODEL, true>(c, a, &tm_a);
 }
 
 // ------------------------------------------------------------------------------------------
@@ -282,7 +318,8 @@ __global__ void __launch_bounds__(P::NT) k_intensity(const PassArgs a) {
 // sc = {fscale, iscale, gscale}
 // ------------------------------------------------------------------------------------------
 template <class P, int MODEL, int WHAT>
-__global__ void __launch_bounds__(P::NT) k_grad(const PassArgs a) {
+__global__ void __launch_bounds__(P::NT) k_grad(const PassArgs a, const __grid_constant__ CUtensorMap tm_a,
+                                                const __grid_constant__ CUtensorMap tm_b) {
   extern __shared__ __align__(128) unsigned char smem_raw[];
   Cta<P> c;
   cta_setup<P>(c, smem_raw, a);
@@ -312,7 +349,9 @@ __global__ void __launch_bounds__(P::NT) k_grad(const PassArgs a) {
     float2* grad_t = a.grad + (size_t)t * g.nz * g.n;
     const float* ii = a.inten_in ? a.inten_in + (size_t)pat * P::N * P::N : nullptr;
     fused_pass<P>(
-        c, [&](int cb, float2(&v)[P::E]) { gather_nat<P>(v, c, cb, psi_t, prb_t, g, p); },
+        c, [&](int cb, float2(&v)[P::E]) {
+          gather_any<P>(v, c, cb, a.use_tma, &tm_a, t, psi_t, prb_t, g, p);
+        },
         [&](int k1, float2(&v)[P::E]) {
           dp_wait<P>(c);
 #pragma unroll
@@ -342,7 +381,9 @@ __global__ void __launch_bounds__(P::NT) k_grad(const PassArgs a) {
 // The first far field of a pair is parked in thread-private scratch while the second is transformed.
 // ------------------------------------------------------------------------------------------
 template <class P, int MODEL>
-__global__ void __launch_bounds__(P::NT) k_linesearch(const PassArgs a) {
+__global__ void __launch_bounds__(P::NT) k_linesearch(const PassArgs a,
+                                                      const __grid_constant__ CUtensorMap tm_a,
+                                                      const __grid_constant__ CUtensorMap tm_b) {
   extern __shared__ __align__(128) unsigned char smem_raw[];
   Cta<P> c;
   cta_setup<P>(c, smem_raw, a);
@@ -363,7 +404,9 @@ __global__ void __launch_bounds__(P::NT) k_linesearch(const PassArgs a) {
       const float2* prb_b = a.prb_b + (size_t)t * a.prb_b_ts + (size_t)j * a.prb_b_ms;
       const bool first = (j == 0), last = (j + 1 == a.npairs);
       spectrum_pass<P>(
-          c, p.skip, [&](int cb, float2(&v)[P::E]) { gather_nat<P>(v, c, cb, psi_a, prb_a, g, p); },
+          c, p.skip, [&](int cb, float2(&v)[P::E]) {
+            gather_any<P>(v, c, cb, a.use_tma, &tm_a, t, psi_a, prb_a, g, p);
+          },
           [&](int k1, float2(&v)[P::E]) {
             float2* st = c.stash + (size_t)k1 * P::E * P::NT + c.tid;
 #pragma unroll
@@ -371,7 +414,9 @@ __global__ void __launch_bounds__(P::NT) k_linesearch(const PassArgs a) {
           },
           [](int) {});
       spectrum_pass<P>(
-          c, p.skip, [&](int cb, float2(&v)[P::E]) { gather_nat<P>(v, c, cb, psi_b, prb_b, g, p); },
+          c, p.skip, [&](int cb, float2(&v)[P::E]) {
+            gather_any<P>(v, c, cb, a.use_tma, &tm_b, t, psi_b, prb_b, g, p);
+          },
           [&](int k1, float2(&v)[P::E]) {
             const float2* st = c.stash + (size_t)k1 * P::E * P::NT + c.tid;
             float* ap = c.accp + (size_t)k1 * P::E * P::NT + c.tid;
@@ -449,8 +494,10 @@ const PlanOps* make_ops() {
     ops.scratch_per_cta = Scratch<P>::TOTAL;
     ops.tw_total = TwLayout<P>::TOTAL;
     ops.fill_tw = fill_tw_host<P>;
+    ops.patch_w = Patch<P>::TMA ? Patch<P>::W : 0;
+    ops.patch_h = Patch<P>::TMA ? Patch<P>::H : 0;
 #define PTX_SET(id, ...)                                   \
-  ops.kernels[id] = (const void*)(void (*)(const PassArgs))(__VA_ARGS__); \
+  ops.kernels[id] = (const void*)(void (*)(const PassArgs, const CUtensorMap, const CUtensorMap))(__VA_ARGS__); \
   ops.names[id] = #__VA_ARGS__;
     PTX_SET(K_FWD, k_fwd<P>)
     PTX_SET(K_NEAR, k_nearplane<P>)
