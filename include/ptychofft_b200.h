@@ -140,6 +140,13 @@ int ptx_vec_dai_yuan_update(const void* g, void* g0, void* d, size_t n, const do
                             int first, void* stream);
 /* y += (*alpha) * x   (ptycho.py:405, 463) */
 int ptx_vec_axpy(void* y, const void* x, size_t n, const float* alpha_dev, void* stream);
+/* y += alpha * x, alpha passed by value (no device scalar to stage) */
+int ptx_vec_axpy_s(void* y, const void* x, size_t n, float alpha, void* stream);
+/* CG scalars on the device, in the reference's float32 arithmetic (ptycho.py:342-351):
+ *   red = {a, b} (doubles)  ->  *s_out = a/b ; sc[0] = fscale = b/a (gaussian) or 1 ; sc[1] = (a/b)^2 */
+int ptx_cg_prep_scale(const double* red, int model, float* s_out, float* sc, void* stream);
+/* sc[2] = k / (*absmax)^2   (ptycho.py:356 with k = 1; 435, 441 with k = nmodes/nscan or 1/nscan) */
+int ptx_cg_prep_gscale(const float* absmax, double k, float* sc, void* stream);
 /* x *= (*s)           (ptycho.py:344) */
 int ptx_vec_scale(void* x, size_t n, const float* s_dev, void* stream);
 /* *out = max(*out, max |x|)   (ptycho.py:356, 435); out caller-zeroed */

@@ -87,6 +87,31 @@ __global__ void k_scale(float2* __restrict__ x, size_t n, const float* s) {
   }
 }
 
+// CG scalars computed where their inputs are (no host round trip), with the reference's float32
+// arithmetic: a, b are CuPy float32 sums; s = a/b; fpsi * (b/a); absfpsi * (a/b)^2 (ptycho.py:342-351)
+__global__ void k_prep_scale(const double* red, int model, float* s_out, float* sc) {
+  const float a = (float)red[0], b = (float)red[1];
+  const float s = a / b;
+  *s_out = s;
+  sc[0] = model == PTX_MODEL_GAUSSIAN ? b / a : 1.f;
+  sc[1] = (float)((double)s * (double)s);
+}
+// sc[2] = k / absmax^2  (ptycho.py:356: / max|probe_k|^2 ; 435, 441: / max|psi|^2 / nscan [* nmodes])
+__global__ void k_prep_gscale(const float* absmax, double k, float* sc) {
+  const double m = (double)*absmax;
+  sc[2] = (float)(k / (m * m));
+}
+__global__ void k_axpy_s(float2* __restrict__ y, const float2* __restrict__ x, size_t n, float al) {
+  for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n;
+       i += (size_t)gridDim.x * blockDim.x) {
+    float2 a = y[i];
+    const float2 b = x[i];
+    a.x += al * b.x;
+    a.y += al * b.y;
+    y[i] = a;
+  }
+}
+
 __global__ void k_absmax(const float2* __restrict__ x, size_t n, float* out) {
   float m = 0.f;
   for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n;
@@ -514,6 +539,30 @@ int ptx_vec_dai_yuan_update(const void* g, void* g0, void* d, size_t n, const do
 int ptx_vec_axpy(void* y, const void* x, size_t n, const float* alpha_dev, void* stream) {
   if (!y || !x || !alpha_dev) return fail(PTX_EINVAL, "ptx_vec_axpy: null array");
   k_axpy<<<vec_grid(n), 256, 0, (cudaStream_t)stream>>>((float2*)y, (const float2*)x, n, alpha_dev);
+  g_launches.fetch_add(1);
+  CUDA_TRY(cudaGetLastError());
+  return PTX_OK;
+}
+
+int ptx_vec_axpy_s(void* y, const void* x, size_t n, float alpha, void* stream) {
+  if (!y || !x) return fail(PTX_EINVAL, "ptx_vec_axpy_s: null array");
+  k_axpy_s<<<vec_grid(n), 256, 0, (cudaStream_t)stream>>>((float2*)y, (const float2*)x, n, alpha);
+  g_launches.fetch_add(1);
+  CUDA_TRY(cudaGetLastError());
+  return PTX_OK;
+}
+
+int ptx_cg_prep_scale(const double* red, int model, float* s_out, float* sc, void* stream) {
+  if (!red || !s_out || !sc) return fail(PTX_EINVAL, "ptx_cg_prep_scale: null array");
+  k_prep_scale<<<1, 1, 0, (cudaStream_t)stream>>>(red, model, s_out, sc);
+  g_launches.fetch_add(1);
+  CUDA_TRY(cudaGetLastError());
+  return PTX_OK;
+}
+
+int ptx_cg_prep_gscale(const float* absmax, double k, float* sc, void* stream) {
+  if (!absmax || !sc) return fail(PTX_EINVAL, "ptx_cg_prep_gscale: null array");
+  k_prep_gscale<<<1, 1, 0, (cudaStream_t)stream>>>(absmax, k, sc);
   g_launches.fetch_add(1);
   CUDA_TRY(cudaGetLastError());
   return PTX_OK;

@@ -268,8 +268,10 @@ class CGPtychoSolver(PtychoCuFFT):
         return self._sum(red)
 
     def _grad(self, what, psi, scan, probe, mode, data, inten, fscale, iscale, gscale, model, out,
-              out_stride=0):
-        sc = self._scalars(fscale, iscale, gscale)
+              out_stride=0, sc=None):
+        """`sc`: device tensor {fscale, iscale, gscale} (then the three host values are ignored)."""
+        if sc is None:
+            sc = self._scalars(fscale, iscale, gscale)
         check(lib.ptx_cg_grad(self._h, what, _ptr(psi), _ptr(scan), _ptr(probe), probe.shape[1],
                               mode, _ptr(data), _ptr(inten) if inten is not None else None,
                               _ptr(sc), model, _ptr(out), out_stride, current_stream()))
@@ -310,8 +312,7 @@ class CGPtychoSolver(PtychoCuFFT):
                                           1 if first else 0, current_stream()))
 
     def _axpy(self, y, x, alpha):
-        a = self._scalars(alpha)
-        check(lib.ptx_vec_axpy(_ptr(y), _ptr(x), y.numel(), _ptr(a), current_stream()))
+        check(lib.ptx_vec_axpy_s(_ptr(y), _ptr(x), y.numel(), float(alpha), current_stream()))
 
     def _absmax(self, x):
         out = torch.zeros(1, dtype=torch.float32, device=x.device)
@@ -436,31 +437,34 @@ class CGPtychoSolver(PtychoCuFFT):
         gradprb0 = torch.zeros_like(gradprb)
         dprb = torch.zeros_like(gradprb)
 
+        s_dev = torch.zeros(1, dtype=torch.float32, device=dev)
+        sc_obj = torch.ones(3, dtype=torch.float32, device=dev)   # {fscale, iscale, gscale}, object pass
+        sc_prb = torch.ones(3, dtype=torch.float32, device=dev)   # {1, 1, gscale}, probe pass
+
         print("# congujate gradient parameters\n"
               "iteration, step size object, step size probe, function min")  # csv column headers
         gammaprb = 0
         self.history = []  # (iteration, step size object, step size probe) -- diagnostics only
         self.ls_log = []   # (first candidate exponent, [f(0), f(2^-c0), ...]) per fused pass
         for i in range(piter):
-            # 1) object retrieval subproblem with fixed probes (ptycho.py:327-345)
-            red = self._intensity(psi, scan, probe, data, inten, mdl).cpu().numpy()
-            a, b = np.float32(red[0]), np.float32(red[1])
-            s = np.float32(a / b)
-            sc = self._scalars(s)
-            check(lib.ptx_vec_scale(_ptr(probe), probe.numel(), _ptr(sc), current_stream()))
-            iscale = float(s) * float(s)                     # absfpsi *= (a/b)**2
+            # 1) object retrieval subproblem with fixed probes (ptycho.py:327-345).  a, b, the probe
+            # rescaling and the gradient scalars stay on the device: no host round trip here
+            red = self._intensity(psi, scan, probe, data, inten, mdl)
+            check(lib.ptx_cg_prep_scale(_ptr(red), mdl, _ptr(s_dev), _ptr(sc_obj), current_stream()))
+            check(lib.ptx_vec_scale(_ptr(probe), probe.numel(), _ptr(s_dev), current_stream()))
             if i % 32 == 0:  # cost of this iteration's absfpsi, printed below (ptycho.py:481-482)
                 if mdl == 0:
-                    fmin = float(s) ** 2 * red[1] - 2.0 * float(s) * red[0] + sum_data
+                    r = red.cpu().numpy()
+                    s = float(np.float32(np.float32(r[0]) / np.float32(r[1])))
+                    fmin = s ** 2 * r[1] - 2.0 * s * r[0] + sum_data
                 else:
                     fmin = float(self._intensity(psi, scan, probe, data, None, mdl)[2])
             # gradient (ptycho.py:346-363)
             gradpsi.zero_()
             for k in range(M):
-                pmax = float(self._absmax(probe[:, k]))
-                fscale = float(np.float32(b / a)) if mdl == 0 else 1.0
-                self._grad(0, psi, scan, probe, k, data, inten, fscale, iscale,
-                           1.0 / (pmax * pmax), mdl, gradpsi)
+                check(lib.ptx_cg_prep_gscale(_ptr(self._absmax(probe[:, k])), 1.0, _ptr(sc_obj),
+                                             current_stream()))
+                self._grad(0, psi, scan, probe, k, data, inten, 0, 0, 0, mdl, gradpsi, sc=sc_obj)
             # Dai-Yuan direction (ptycho.py:364-372)
             self._dai_yuan(gradpsi, gradpsi0, dpsi, i == 0)
             # line search (ptycho.py:374-393)
@@ -477,13 +481,12 @@ class CGPtychoSolver(PtychoCuFFT):
                     # 2) probe retrieval subproblem with fixed object (ptycho.py:420-441)
                     if multi:
                         self._intensity(psi, scan, probe, data, inten, mdl)
-                    psimax = float(self._absmax(psi))
-                    gscale = 1.0 / (psimax * psimax) / S
-                    if mdl == 0:
-                        gscale *= M
+                    kg = (float(M) if mdl == 0 else 1.0) / S      # Q13: * nmodes only for gaussian
+                    check(lib.ptx_cg_prep_gscale(_ptr(self._absmax(psi)), kg, _ptr(sc_prb),
+                                                 current_stream()))
                     gradprb[m].zero_()
-                    self._grad(1, psi, scan, probe, m, data, inten, 1.0, 1.0, gscale, mdl,
-                               gradprb[m], P * P)
+                    self._grad(1, psi, scan, probe, m, data, inten, 0, 0, 0, mdl, gradprb[m], P * P,
+                               sc=sc_prb)
                     if self.comm is not None:
                         self.comm.probe_grad_(gradprb[m])
                     # Dai-Yuan direction (ptycho.py:442-450)

@@ -42,6 +42,9 @@ SYMBOLS = [
     ("ptx_vec_dai_yuan_reduce", _i, [_vp, _vp, _vp, _sz, _dp, _vp]),
     ("ptx_vec_dai_yuan_update", _i, [_vp, _vp, _vp, _sz, _dp, _i, _vp]),
     ("ptx_vec_axpy", _i, [_vp, _vp, _sz, _fp, _vp]),
+    ("ptx_vec_axpy_s", _i, [_vp, _vp, _sz, ctypes.c_float, _vp]),
+    ("ptx_cg_prep_scale", _i, [_dp, _i, _fp, _fp, _vp]),
+    ("ptx_cg_prep_gscale", _i, [_fp, ctypes.c_double, _fp, _vp]),
     ("ptx_vec_scale", _i, [_vp, _sz, _fp, _vp]),
     ("ptx_vec_absmax", _i, [_vp, _sz, _fp, _vp]),
 ]
