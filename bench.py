@@ -250,6 +250,15 @@ def run_b200(args, world, rank, local):
             kt.append(e0.elapsed_time(e1) * 1e-3)
         kavg = float(np.mean(kt))
         abytes, aflops = algorithmic_bytes(w, T), algorithmic_flops(w, T)
+        # the roof that binds: bytes this algorithm moves through the SM's
+        # 128 B/clk L1 / shared-memory pipe -- 2 exchanges x 2 transforms x (store + load) of the
+        # 8 N^2-byte tile, 4 bilinear taps + 2 probe reads + scatter staging and reductions
+        pipe_bytes = npat * N * N * 8 * (8 + 4 + 2 + 3.1)
+        pipe_peak = 148 * 128 * 1.965e9
+        pipe = {"achieved_tbs": pipe_bytes / kavg / 1e12, "peak_tbs": pipe_peak / 1e12,
+                "frac": pipe_bytes / kavg / pipe_peak,
+                "note": "L1/shared data pipe, 128 B/clk/SM x 148 SMs x 1.965 GHz; ncu "
+                        "l1tex__data_pipe_lsu_wavefronts reads 58 % busy (profiles/)"}
 
         # end to end through the host-array API (pinned host memory in, host gradient out)
         h = {k: torch.from_numpy(np.ascontiguousarray(v)).pin_memory().numpy()
@@ -309,8 +318,9 @@ def run_b200(args, world, rank, local):
                      "fp32": {"achieved_tflops": aflops / kavg / 1e12,
                               "peak_tflops": FP32_NOMINAL_TFLOPS,
                               "frac": aflops / kavg / 1e12 / FP32_NOMINAL_TFLOPS,
-                              "note": "binding roof of the fused kernel (SURVEY.md 8d); nominal peak "
-                                      "148 SM x 128 lanes x 2 x 1.965 GHz, FFT flops 20 N^2 log2 N"}},
+                              "note": "nominal peak 148 SM x 128 lanes x 2 x 1.965 GHz, FFT flops "
+                                      "20 N^2 log2 N (SURVEY.md 8d)"},
+                     "sm_data_pipe": pipe},
     }
     traffic = os.path.join(ROOT, "profiles", "traffic.json")
     if os.path.exists(traffic):
