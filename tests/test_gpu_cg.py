@@ -217,3 +217,40 @@ def test_cg_cost_decreases_c2():
         res = slv.run(d, psi0, s, p.clone(), piter=16, model="gaussian", recover_prb=False)
         c1 = float(slv._intensity(res["psi"], s, res["probe"], d, None, 0)[2])
     assert c1 < 0.2 * c0
+
+
+@pytest.mark.skipif(not ref_gpu.available(), reason="oracle/_ref not built")
+@pytest.mark.parametrize("ndet,nprb,model", [(128, 96, "gaussian"), (64, 64, "poisson"), (256, 256, "gaussian")])
+def test_cg_skipped_positions_window_and_two_angles(ndet, nprb, model):
+    """Edge cases of the solver against the reference's cuFFT path: positions flagged -1 (skipped,
+    tests/test_fsc.py:16-17) including the first and the last pattern of the batch, a probe window
+    smaller than the detector, and ptheta = 2 (CG scalars global over both angles)."""
+    pt = _pt()
+    T, side = 2, 4
+    nz, n = nprb + 70, nprb + 90
+    w = workloads.synth_angles(T, nz, n, ndet, nprb, side, 1, seed0=21)
+    psi, scan, probe = w["psi"], w["scan"].copy(), w["probe"]
+    S = side * side
+    data = np.stack([np.abs(O.fwd(psi[t:t + 1], scan[t:t + 1], np.ascontiguousarray(probe[t:t + 1, 0]),
+                                  ndet))[0] ** 2 for t in range(T)]).astype(np.float32)
+    scan[0, 0] = -1.0          # first pattern of the batch
+    scan[0, 5] = (-1.0, 3.0)
+    scan[1, S - 1] = -1.0      # last pattern of the batch
+    psi0 = np.ones_like(psi)
+    prb0 = (probe * (0.9 + 0.1j)).astype(np.complex64)
+    piter = 3
+    with ref_gpu.RefCGPtychoSolver(S, nprb, ndet, T, nz, n) as ref:
+        want = ref.run_batch(data, psi0, scan, prb0, piter=piter, model=model, recover_prb=True,
+                             verbose=False)
+        steps = [t[2] for t in ref.last_trials]
+
+    def exact():
+        with O.float64_arithmetic():
+            return O.cg_run(data, psi0, scan, prb0.copy(), piter, model, True, ndet=ndet,
+                            forced_steps=list(steps))
+
+    with pt.CGPtychoSolver(S, nprb, ndet, T, nz, n) as slv:
+        slv._forced_steps = list(steps)
+        got = slv.run_batch(data, psi0, scan, prb0, piter=piter, model=model, recover_prb=True)
+        same = _assert_parity(got, want, exact, "(skips, window, ptheta=2) %s" % ((ndet, nprb, model),))
+        _audit_decisions(slv, steps, strict=same)
