@@ -218,8 +218,7 @@ static EncodeTiledFn encode_fn() {
 }
 static bool make_object_map(const ptx_plan* p, const void* psi, CUtensorMap* tm) {
   const PlanOps* ops = p->ops;
-  static const bool off = getenv("PTX_NO_TMA_GATHER") != nullptr;
-  if (off || !ops->patch_w || !psi || ((uintptr_t)psi & 15) || (p->n & 1) || !encode_fn()) return false;
+  if (!ops->patch_w || !psi || ((uintptr_t)psi & 15) || (p->n & 1) || !encode_fn()) return false;
   const cuuint64_t dims[3] = {p->n, p->nz, p->ptheta};
   const cuuint64_t strides[2] = {p->n * 8, p->n * p->nz * 8};
   const cuuint32_t box[3] = {(cuuint32_t)ops->patch_w, (cuuint32_t)ops->patch_h, 1};
@@ -237,12 +236,16 @@ static int launch(ptx_plan* p, int kid, PassArgs& a, cudaStream_t st) {
   memset(&tm_a, 0, sizeof(tm_a));
   memset(&tm_b, 0, sizeof(tm_b));
   a.use_tma = 0;
-  // TMA patch gather pays where measured (profiles/): every forward-only pass of the multi-block
-  // plans (N = 256) and the line search; elsewhere the strided read-only loads are as fast
-  static const bool force = getenv("PTX_TMA_GATHER_ALL") != nullptr;
+  // PTX_TMA_GATHER = sel (default: where the prefetched tensor copy measured faster than strided
+  // loads -- intensity and line-search passes, and the forward operator of the multi-block plans;
+  // profiles/) | all | off
+  static const int policy = []() {
+    const char* e = getenv("PTX_TMA_GATHER");
+    return !e ? 1 : !strcmp(e, "off") ? 0 : !strcmp(e, "all") ? 2 : 1;
+  }();
   const bool ls = (kid == K_LS_GAUSS || kid == K_LS_POIS);
-  const bool fwd_only = ls || kid == K_FWD || kid == K_INT_GAUSS || kid == K_INT_POIS;
-  const bool want = force || ls || (ops->RC > 1 && fwd_only);
+  const bool inten = (kid == K_INT_GAUSS || kid == K_INT_POIS);
+  const bool want = policy == 2 || (policy == 1 && (ls || inten || (ops->RC > 1 && kid == K_FWD)));
   if (want && kid != K_NEAR && kid != K_ADJ_OBJ && kid != K_ADJ_PRB && a.psi) {
     const bool two = (kid == K_LS_GAUSS || kid == K_LS_POIS);
     if (make_object_map(p, a.psi, &tm_a) && (!two || make_object_map(p, a.psi_b, &tm_b))) a.use_tma = 1;

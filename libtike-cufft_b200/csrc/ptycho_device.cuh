@@ -95,6 +95,7 @@ struct Cta {
   unsigned phase;      // parity of the next dbuf completion to wait for
   unsigned phase2;     // ... of the next patch completion
   int pshift;          // 0/1: column offset of the patch inside its (even-aligned) TMA box
+  int pp_key;          // key (2*pattern + object) of the block-0 patch in flight / landed, or -1
   double* slots;       // global thread-private running sums: slots[k * NT], k < 9
   float2* frame;       // global scratch frame [RC][NY][NX] (RC > 1 only)
   float2* stash;       // global thread-private scratch, N*N complex: [(k*E + e)*NT + tid]
@@ -123,6 +124,7 @@ __device__ __forceinline__ void dp_init(Cta<P>& c) {
   }
   c.phase = 0;
   c.phase2 = 0;
+  c.pp_key = -1;
 }
 __device__ __forceinline__ void mbar_wait(unsigned bar, unsigned phase) {
   unsigned done = 0;
@@ -522,12 +524,12 @@ __device__ __forceinline__ void inverse_pass(Cta<P>& c, Load load, Near near) {
 // in registers (2 shared loads per output pixel) and issues ONE vector reduction
 // (red.global.add.v2.f32) per object pixel instead of the reference's 8 scalar atomics per probe
 // pixel (kernels.cu:73-80).  The column to the right of the block only receives the gam * t part
-// (the neighbouring block adds its own share: the adds commute).  Leaves the tile free (trailing barrier).
-template <class P, bool FULL>
+// (the neighbouring block adds its own share: the adds commute).  Leaves the tile free.
+template <class P, bool FULL, class TileFree>
 __device__ __forceinline__ void scatter_impl(float2 (&v)[P::E], const Cta<P>& c, int cb,
                                              const float2* __restrict__ prb, float scale,
                                              float2* __restrict__ grad_t, const Geo& g,
-                                             const Pat& p) {
+                                             const Pat& p, TileFree tile_free) {
   // FULL: probe window == frame and the (P+1)^2 footprint lies inside the object: no predicates.
   constexpr int ROWS = P::N, COLS = Cross<P>::CW;
   constexpr int PITCH = TileGeom<P>::WORDS / ROWS;
@@ -598,16 +600,18 @@ __device__ __forceinline__ void scatter_impl(float2 (&v)[P::E], const Cta<P>& c,
     }
   }
   __syncthreads();
+  tile_free();
 }
-template <class P>
+// tile_free(): called by every thread once the tile is no longer needed (after a block barrier)
+template <class P, class TileFree>
 __device__ __forceinline__ void scatter_block(float2 (&v)[P::E], const Cta<P>& c, int cb,
                                               const float2* __restrict__ prb, float scale,
                                               float2* __restrict__ grad_t, const Geo& g,
-                                              const Pat& p) {
+                                              const Pat& p, TileFree tile_free) {
   if (g.P == P::N && p.inside)
-    scatter_impl<P, true>(v, c, cb, prb, scale, grad_t, g, p);
+    scatter_impl<P, true>(v, c, cb, prb, scale, grad_t, g, p, tile_free);
   else
-    scatter_impl<P, false>(v, c, cb, prb, scale, grad_t, g, p);
+    scatter_impl<P, false>(v, c, cb, prb, scale, grad_t, g, p, tile_free);
 }
 
 // ---------------------------------------------------------------- probe adjoint

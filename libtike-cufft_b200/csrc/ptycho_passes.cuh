@@ -103,18 +103,22 @@ __device__ __forceinline__ float minf_px(float x, float d, float sqd) {
 
 // near plane of column block cb: object patch by TMA tensor copy when the tensor map is usable,
 // strided read-only loads otherwise (odd object width, unaligned base, 512^2 detectors).
-// With several column blocks (N > 128) the copy of block cb+1 is issued as soon as block cb's taps
-// have been read, so that it overlaps the cross butterfly and the frame stores of block cb.
+// The copy is pipelined: block 0 of a pattern is normally already in flight (patch_prefetch, issued
+// when the previous tile user released the tile), and the copy of block cb+1 is issued as soon as
+// block cb's taps have been read, overlapping the cross butterfly and the frame stores.
 template <class P>
 __device__ __forceinline__ void gather_any(float2 (&v)[P::E], Cta<P>& c, int cb, bool use_tma,
-                                           const CUtensorMap* tm, int t,
+                                           const CUtensorMap* tm, int key, int t,
                                            const float2* __restrict__ psi_t,
                                            const float2* __restrict__ prb, const Geo& g,
                                            const Pat& p) {
   if (Patch<P>::TMA && use_tma) {
     if (cb == 0) {
-      __syncthreads();  // every thread is done with the tile (e.g. the last inverse stage's loads)
-      patch_issue<P>(c, tm, g, p, t, 0);
+      if (c.pp_key != key) {
+        __syncthreads();  // every thread is done with the tile (e.g. the last inverse stage's loads)
+        patch_issue<P>(c, tm, g, p, t, 0);
+      }
+      c.pp_key = -1;
     }
     const int shift = c.pshift;
     gather_tma<P>(v, c, cb, shift, prb, g, p);  // ends with a block barrier: the tile is free again
@@ -122,6 +126,18 @@ __device__ __forceinline__ void gather_any(float2 (&v)[P::E], Cta<P>& c, int cb,
   } else {
     gather_nat<P>(v, c, cb, psi_t, prb, g, p);
   }
+}
+// Issue block 0 of pattern `pat`'s patch ahead of time.  To be called by every thread right after a
+// block barrier that released the tile; nothing may touch the tile until that pattern's gather.
+template <class P>
+__device__ __forceinline__ void patch_prefetch(Cta<P>& c, bool use_tma, const CUtensorMap* tm, int key,
+                                               int pat, int npat, const float2* __restrict__ scan,
+                                               const Geo& g) {
+  if (!(Patch<P>::TMA && use_tma) || pat >= npat) return;
+  const Pat p = make_pat(scan, pat, g);
+  if (p.skip) return;
+  patch_issue<P>(c, tm, g, p, pat / g.S, 0);
+  c.pp_key = key;
 }
 
 // re-arm the data pipe with the tile that follows (pat, k1) in this CTA's schedule
@@ -154,13 +170,16 @@ __global__ void __launch_bounds__(P::NT) k_fwd(const PassArgs a, const __grid_co
     const float2* prb_t = a.prb + (size_t)t * a.prb_ts;
     spectrum_pass<P>(
         c, p.skip, [&](int cb, float2(&v)[P::E]) {
-          gather_any<P>(v, c, cb, a.use_tma, &tm_a, t, psi_t, prb_t, g, p);
+          gather_any<P>(v, c, cb, a.use_tma, &tm_a, 2 * pat, t, psi_t, prb_t, g, p);
         },
         [&](int k1, float2(&v)[P::E]) {
 #pragma unroll
           for (int e = 0; e < P::E; ++e) out[spec_index<P>(c, k1, e)] = v[e];
         },
-        [](int) {});
+        [&](int k1) {
+          if (k1 == P::RC - 1)
+            patch_prefetch<P>(c, a.use_tma, &tm_a, 2 * (pat + gridDim.x), pat + gridDim.x, npat, a.scan, g);
+        });
   }
 }
 
@@ -231,7 +250,7 @@ __global__ void __launch_bounds__(P::NT) k_adj(const PassArgs a, const __grid_co
         },
         [&](int cb, float2(&v)[P::E]) {
           if (FLG == 0)
-            scatter_block<P>(v, c, cb, prb_t, g.kappa, grad_t, g, p);
+            scatter_block<P>(v, c, cb, prb_t, g.kappa, grad_t, g, p, []() {});
           else
             pacc_add<P>(v, c, cb, psi_t, g.kappa, g, p);
         });
@@ -260,7 +279,7 @@ __device__ __forceinline__ void intensity_body(Cta<P>& c, const PassArgs& a, con
       const bool first = !MULTI || (k == kfirst), last = !MULTI || (k + 1 == a.nmodes);
       spectrum_pass<P>(
           c, p.skip, [&](int cb, float2(&v)[P::E]) {
-            gather_any<P>(v, c, cb, a.use_tma, tm, t, psi_t, prb_k, g, p);
+            gather_any<P>(v, c, cb, a.use_tma, tm, 2 * pat, t, psi_t, prb_k, g, p);
           },
           [&](int k1, float2(&v)[P::E]) {
             float* ia = c.accp + (size_t)k1 * P::E * P::NT + c.tid;
@@ -291,6 +310,10 @@ __device__ __forceinline__ void intensity_body(Cta<P>& c, const PassArgs& a, con
           },
           [&](int k1) {
             if (last) dp_next<P>(c, a.data, pat, k1, npat);
+            if (k1 == P::RC - 1) {  // the tile is free: next mode of this pattern, or the next pattern
+              const int np = last ? pat + (int)gridDim.x : pat;
+              patch_prefetch<P>(c, a.use_tma, tm, 2 * np, np, npat, a.scan, g);
+            }
           });
     }
   }
@@ -350,7 +373,7 @@ __global__ void __launch_bounds__(P::NT) k_grad(const PassArgs a, const __grid_c
     const float* ii = a.inten_in ? a.inten_in + (size_t)pat * P::N * P::N : nullptr;
     fused_pass<P>(
         c, [&](int cb, float2(&v)[P::E]) {
-          gather_any<P>(v, c, cb, a.use_tma, &tm_a, t, psi_t, prb_t, g, p);
+          gather_any<P>(v, c, cb, a.use_tma, &tm_a, 2 * pat, t, psi_t, prb_t, g, p);
         },
         [&](int k1, float2(&v)[P::E]) {
           dp_wait<P>(c);
@@ -364,10 +387,20 @@ __global__ void __launch_bounds__(P::NT) k_grad(const PassArgs a, const __grid_c
             v[e].y *= f;
           }
         },
-        [&](int k1) { dp_next<P>(c, a.data, pat, k1, npat); },
+        [&](int k1) {
+          dp_next<P>(c, a.data, pat, k1, npat);
+          if (WHAT == 1 && P::RC == 1 && Patch<P>::TMA && a.use_tma) {  // probe pass: the tile is idle after the inverse
+            __syncthreads();
+            patch_prefetch<P>(c, a.use_tma, &tm_a, 2 * (pat + gridDim.x), pat + gridDim.x, npat, a.scan, g);
+          }
+        },
         [&](int cb, float2(&v)[P::E]) {
           if (WHAT == 0)
-            scatter_block<P>(v, c, cb, prb_t, gscale, grad_t, g, p);
+            scatter_block<P>(v, c, cb, prb_t, gscale, grad_t, g, p, [&]() {
+              if (cb == P::RC - 1)
+                patch_prefetch<P>(c, a.use_tma, &tm_a, 2 * (pat + gridDim.x), pat + gridDim.x, npat,
+                                  a.scan, g);
+            });
           else
             pacc_add<P>(v, c, cb, psi_t, gscale, g, p);
         });
@@ -405,17 +438,19 @@ __global__ void __launch_bounds__(P::NT) k_linesearch(const PassArgs a,
       const bool first = (j == 0), last = (j + 1 == a.npairs);
       spectrum_pass<P>(
           c, p.skip, [&](int cb, float2(&v)[P::E]) {
-            gather_any<P>(v, c, cb, a.use_tma, &tm_a, t, psi_a, prb_a, g, p);
+            gather_any<P>(v, c, cb, a.use_tma, &tm_a, 2 * pat, t, psi_a, prb_a, g, p);
           },
           [&](int k1, float2(&v)[P::E]) {
             float2* st = c.stash + (size_t)k1 * P::E * P::NT + c.tid;
 #pragma unroll
             for (int e = 0; e < P::E; ++e) st[e * P::NT] = v[e];
           },
-          [](int) {});
+          [&](int k1) {  // the second object's patch of the same pattern comes next
+            if (k1 == P::RC - 1) patch_prefetch<P>(c, a.use_tma, &tm_b, 2 * pat + 1, pat, npat, a.scan, g);
+          });
       spectrum_pass<P>(
           c, p.skip, [&](int cb, float2(&v)[P::E]) {
-            gather_any<P>(v, c, cb, a.use_tma, &tm_b, t, psi_b, prb_b, g, p);
+            gather_any<P>(v, c, cb, a.use_tma, &tm_b, 2 * pat + 1, t, psi_b, prb_b, g, p);
           },
           [&](int k1, float2(&v)[P::E]) {
             const float2* st = c.stash + (size_t)k1 * P::E * P::NT + c.tid;
@@ -463,6 +498,10 @@ __global__ void __launch_bounds__(P::NT) k_linesearch(const PassArgs a,
           },
           [&](int k1) {
             if (last) dp_next<P>(c, a.data, pat, k1, npat);
+            if (k1 == P::RC - 1) {  // next pair of this pattern, or the next pattern: first object
+              const int np = last ? pat + (int)gridDim.x : pat;
+              patch_prefetch<P>(c, a.use_tma, &tm_a, 2 * np, np, npat, a.scan, g);
+            }
           });
     }
   }
