@@ -199,20 +199,54 @@ class PtychoCuFFT(ptychofft):
         raise NotImplementedError("Cannot run a base class.")
 
     def run_batch(self, data, psi, scan, probe, **kwargs):
-        """Run by dividing the work into batches of ptheta angles, ptycho.py:135-162."""
+        """Run by dividing the work into batches of ptheta angles, ptycho.py:135-162.
+
+        Same contract as the reference (host arrays in, copies of psi / probe out, trailing
+        `ntheta % ptheta` angles left untouched, Q9).  The host <-> device shuffle is pipelined: the
+        inputs of chunk k+1 are staged through pinned memory and copied on a side stream while
+        chunk k is being reconstructed, and results are read back asynchronously.
+        """
         assert probe.ndim == 4, "probe needs 4 dimensions, not %d" % probe.ndim
         psi = psi.copy()
         probe = probe.copy()
         T = self.ptheta
-        for k in range(0, scan.shape[0] // T):
+        nchunk = scan.shape[0] // T
+        if nchunk == 0:
+            return {"psi": psi, "probe": probe}
+        copy_stream = torch.cuda.Stream()
+        main = torch.cuda.current_stream()
+
+        def stage(k):
             ids = slice(k * T, (k + 1) * T)
-            psi_gpu = torch.from_numpy(np.ascontiguousarray(psi[ids])).cuda()
-            scan_gpu = torch.from_numpy(np.ascontiguousarray(scan[ids])).cuda()
-            prb_gpu = torch.from_numpy(np.ascontiguousarray(probe[ids])).cuda()
-            data_gpu = torch.from_numpy(np.ascontiguousarray(data[ids])).cuda()
+            with torch.cuda.stream(copy_stream):
+                dev = [torch.from_numpy(np.ascontiguousarray(x[ids])).pin_memory().cuda(non_blocking=True)
+                       for x in (data, psi, scan, probe)]
+                ev = torch.cuda.Event()
+                ev.record(copy_stream)
+            return ids, dev, ev
+
+        pending = []  # (ids, pinned psi, pinned probe, event) of results in flight
+        nxt = stage(0)
+        for k in range(nchunk):
+            ids, (data_gpu, psi_gpu, scan_gpu, prb_gpu), ev = nxt
+            main.wait_event(ev)
+            if k + 1 < nchunk:
+                nxt = stage(k + 1)
             result = self.run(data_gpu, psi_gpu, scan_gpu, prb_gpu, **kwargs)
-            psi[ids] = result["psi"].cpu().numpy()
-            probe[ids] = result["probe"].cpu().numpy()
+            h_psi = torch.empty(result["psi"].shape, dtype=torch.complex64).pin_memory()
+            h_prb = torch.empty(result["probe"].shape, dtype=torch.complex64).pin_memory()
+            h_psi.copy_(result["psi"], non_blocking=True)
+            h_prb.copy_(result["probe"], non_blocking=True)
+            done = torch.cuda.Event()
+            done.record(main)
+            pending.append((ids, h_psi, h_prb, done, result))
+            while len(pending) > 1:  # drain all but the newest
+                i0, a, b, e, _ = pending.pop(0)
+                e.synchronize()
+                psi[i0], probe[i0] = a.numpy(), b.numpy()
+        for i0, a, b, e, _ in pending:
+            e.synchronize()
+            psi[i0], probe[i0] = a.numpy(), b.numpy()
         return {"psi": psi, "probe": probe}
 
 

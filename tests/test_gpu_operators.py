@@ -261,3 +261,37 @@ def test_c2_full_size_properties():
         b = torch.sum(g1 * torch.conj(g1))
         c = torch.sum(prb * torch.conj(q))
         assert abs(a - b) / abs(a) < 1e-5 and abs(a - c) / abs(a) < 1e-5
+
+
+@pytest.mark.parametrize("ndet,nmodes,model", [(128, 1, "gaussian"), (64, 3, "poisson"), (256, 1, "gaussian")])
+def test_grad_ptycho_batch_vs_oracle(ndet, nmodes, model):
+    """The host-array fused gradient (what bench.py's e2e leg times): for every angle
+    sum_k Q_k* F* [F Q_k psi (1 - sqrt(d)/sqrt(I))]  (gaussian; 1 - d/I for poisson), against the
+    NumPy restatement of fwd / adj.  3 angles through a ptheta = 1 plan = 3 pipelined chunks."""
+    pt = _pt()
+    T, side = 3, 3
+    nz, n = ndet + 40, ndet + 52
+    w = workloads.synth_angles(T, nz, n, ndet, ndet, side, nmodes, seed0=9)
+    psi, scan, probe = w["psi"], w["scan"], w["probe"]
+    rng = np.random.default_rng(5)
+    data = np.zeros((T, side * side, ndet, ndet), dtype=np.float32)
+    for k in range(nmodes):
+        data += np.abs(O.fwd(psi, scan, np.ascontiguousarray(probe[:, k]), ndet)) ** 2
+    data *= rng.uniform(0.7, 1.3, data.shape).astype(np.float32)  # make the residual non-trivial
+    psi1 = (psi * (0.8 + 0.3j)).astype(np.complex64)
+    want = np.zeros_like(psi1)
+    inten = np.zeros_like(data)
+    far = [O.fwd(psi1, scan, np.ascontiguousarray(probe[:, k]), ndet) for k in range(nmodes)]
+    for f in far:
+        inten += np.abs(f) ** 2
+    for k, f in enumerate(far):
+        if model == "gaussian":
+            r = f - np.sqrt(data) * f / (np.sqrt(inten) + np.float32(1e-32))
+        else:
+            r = f - data * f / (inten + np.float32(1e-32))
+        want += O.adj(r.astype(np.complex64), scan, np.ascontiguousarray(probe[:, k]), nz, n)
+    with pt.CGPtychoSolver(side * side, ndet, ndet, 1, nz, n) as slv:
+        got = slv.grad_ptycho_batch(data, psi1, scan, probe, model=model)
+        got2 = slv.grad_ptycho_batch(data, psi1, scan, probe, model=model)  # buffers are reused
+    assert rel_l2(got, want) < 2e-5
+    assert rel_l2(got2, want) < 2e-5
