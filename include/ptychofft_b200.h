@@ -127,6 +127,29 @@ int ptx_cg_linesearch(ptx_plan* p, const void* obj_a, const void* prb_a, int nmo
                       int ncand, double* cost, void* stream);
 
 /* ---------------------------------------------------------------------------------------
+ * Position correction (ptycho.py:163-248, called from the CG loop at ptycho.py:398-403).
+ * ------------------------------------------------------------------------------------- */
+
+/* register_translation_batch(src_image, target_image, upsample_factor, space), ptycho.py:192-248:
+ * phase correlation of nimg pairs of N x N complex64 images (N = the plan's detector size) with the
+ * reference's upsampled matrix-DFT refinement (_upsampled_dft_batch, ptycho.py:163-190, complex128).
+ * fourier_space != 0: the inputs already are Fourier transforms (space='fourier'); else they are
+ * transformed first (space='real').  shifts: [nimg][2] doubles (row, col), fully overwritten.
+ * upsample_factor: integer in [1, 100].  The reference's trailing `shape[dim] == 1` loop (which
+ * zeroes the shifts of a batch of ONE image) is left to the caller (the Python mirror does it). */
+int ptx_register_translation(ptx_plan* p, const void* src, const void* target, size_t nimg,
+                             int fourier_space, int upsample_factor, double* shifts, void* stream);
+
+/* The fused position-correction step of CGPtychoSolver.run (ptycho.py:398-403):
+ *   tmp1 = fwd(psi_a, scan, ones)[0] ; tmp2 = fwd(psi_b, scan, ones)[0]
+ *   shifts = register_translation_batch(tmp1, tmp2, upsample_factor, space='fourier')
+ * for the nscan positions of angle 0, without materialising either far field.  psi_a, psi_b:
+ * [nz,n] complex64 (angle 0); scan: [nscan,2]; shifts: [nscan][2] doubles.  Skipped positions
+ * (negative integer part) get the reference's all-zero-argmax value -dftshift/upsample_factor. */
+int ptx_cg_position_shifts(ptx_plan* p, const void* psi_a, const void* psi_b, const void* scan,
+                           int upsample_factor, double* shifts, void* stream);
+
+/* ---------------------------------------------------------------------------------------
  * Small fused vector kernels on object / probe sized complex arrays (n complex elements),
  * replacing the CuPy temporaries of ptycho.py:344, 356, 366-372, 405, 435, 444-450, 463.
  * ------------------------------------------------------------------------------------- */

@@ -1,5 +1,5 @@
 // Kernel family for detector size 2^9 (see ptycho_passes.cuh); one translation unit per size.
-#include "ptycho_passes.cuh"
+#include "ptycho_register.cuh"
 
 namespace ptx {
 const PlanOps* ops_l9() { return make_ops<Plan<9>>(); }

@@ -157,6 +157,10 @@ struct ptx_plan {
   float2* scratch;
   size_t scratch_per_cta;  // float2
   Geo geo;
+  // position correction (lazy): E table of the last upsampling factor, all-ones probe
+  double2* reg_E;
+  int reg_uf;
+  float2* ones;
 };
 
 static const PlanOps* ops_for(int L) {
@@ -176,9 +180,11 @@ static int plan_init(ptx_plan* p) {
   CUDA_TRY(cudaMalloc(&p->tw, tw.size() * sizeof(float2)));
   CUDA_TRY(cudaMemcpy(p->tw, tw.data(), tw.size() * sizeof(float2), cudaMemcpyHostToDevice));
   // opt in to the large dynamic shared-memory carve-out for every kernel of this size class
-  for (int k = 0; k < K_COUNT; ++k)
-    CUDA_TRY(cudaFuncSetAttribute(ops->kernels[k], cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                  (int)ops->smem_bytes));
+  for (int k = 0; k < K_COUNT; ++k) {
+    const bool reg = k == K_REG_OBJ || k == K_REG_FOURIER || k == K_REG_REAL;
+    const size_t bytes = reg && ops->smem_bytes_reg > ops->smem_bytes ? ops->smem_bytes_reg : ops->smem_bytes;
+    CUDA_TRY(cudaFuncSetAttribute(ops->kernels[k], cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes));
+  }
   // persistent grid: as many CTAs as fit at once
   int per_sm = 0;
   CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, ops->kernels[K_GRAD_GAUSS_OBJ],
@@ -228,6 +234,8 @@ static bool make_object_map(const ptx_plan* p, const void* psi, CUtensorMap* tm)
                      CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
 }
 
+static bool reg_kernel(int kid) { return kid == K_REG_OBJ || kid == K_REG_FOURIER || kid == K_REG_REAL; }
+
 static int launch(ptx_plan* p, int kid, PassArgs& a, cudaStream_t st) {
   const PlanOps* ops = p->ops;
   const int npat = a.g.T * a.g.S;
@@ -246,14 +254,16 @@ static int launch(ptx_plan* p, int kid, PassArgs& a, cudaStream_t st) {
   const bool ls = (kid == K_LS_GAUSS || kid == K_LS_POIS);
   const bool inten = (kid == K_INT_GAUSS || kid == K_INT_POIS);
   const bool want = policy == 2 || (policy == 1 && (ls || inten || (ops->RC > 1 && kid == K_FWD)));
-  if (want && kid != K_NEAR && kid != K_ADJ_OBJ && kid != K_ADJ_PRB && a.psi) {
+  if (want && kid != K_NEAR && kid != K_ADJ_OBJ && kid != K_ADJ_PRB && !reg_kernel(kid) && a.psi) {
     const bool two = (kid == K_LS_GAUSS || kid == K_LS_POIS);
     if (make_object_map(p, a.psi, &tm_a) && (!two || make_object_map(p, a.psi_b, &tm_b))) a.use_tma = 1;
   }
   void* params[] = {&a, &tm_a, &tm_b};
   const bool nodata = kid == K_FWD || kid == K_NEAR || kid == K_ADJ_OBJ || kid == K_ADJ_PRB;
+  const bool reg = kid == K_REG_OBJ || kid == K_REG_FOURIER || kid == K_REG_REAL;
   cudaError_t e = cudaLaunchKernel(ops->kernels[kid], dim3(grid), dim3(ops->NT), params,
-                                   nodata ? ops->smem_bytes_nodata : ops->smem_bytes, st);
+                                   reg ? ops->smem_bytes_reg
+                                       : nodata ? ops->smem_bytes_nodata : ops->smem_bytes, st);
   g_launches.fetch_add(1);
   if (e != cudaSuccess) return fail(PTX_ECUDA, "launch %s: %s", ops->names[kid], cudaGetErrorString(e));
   CUDA_TRY(cudaGetLastError());
@@ -322,6 +332,9 @@ int ptx_create(ptx_plan** out, size_t ptheta, size_t nz, size_t n, size_t nscan,
   p->freed = false;
   p->tw = nullptr;
   p->scratch = nullptr;
+  p->reg_E = nullptr;
+  p->reg_uf = 0;
+  p->ones = nullptr;
   p->geo.T = (int)ptheta; p->geo.nz = (int)nz; p->geo.n = (int)n; p->geo.S = (int)nscan;
   p->geo.P = (int)nprb; p->geo.N = (int)ndet; p->geo.o = (int)((ndet - nprb) / 2);
   p->geo.kappa = 1.0f / (float)ndet;
@@ -353,8 +366,12 @@ int ptx_free(ptx_plan* p) {
   if (!p->freed) {
     cudaFree(p->tw);
     cudaFree(p->scratch);
+    if (p->reg_E) cudaFree(p->reg_E);
+    if (p->ones) cudaFree(p->ones);
     p->tw = nullptr;
     p->scratch = nullptr;
+    p->reg_E = nullptr;
+    p->ones = nullptr;
     p->freed = true;
   }
   return PTX_OK;
@@ -512,6 +529,87 @@ int ptx_cg_linesearch(ptx_plan* p, const void* obj_a, const void* prb_a, int nmo
   if (model == PTX_MODEL_GAUSSIAN) return launch(p, K_LS_GAUSS, a, st);
   if (model == PTX_MODEL_POISSON) return launch(p, K_LS_POIS, a, st);
   return fail(PTX_EINVAL, "unknown model %d", model);
+}
+
+// ------------------------------------------------------------------------------------------
+// position correction (ptycho_register.cuh)
+// ------------------------------------------------------------------------------------------
+// E[j][k] = exp(2 pi i j k_signed / (uf N)), j < U; zero rows up to REG_EROWS.  Rebuilt (stream
+// ordered) only when the upsampling factor changes.
+static int reg_prepare(ptx_plan* p, int uf, int* U_out, cudaStream_t st) {
+  if (uf < 1) return fail(PTX_EINVAL, "upsample_factor must be a positive integer");
+  const int U = (3 * uf + 1) / 2;  // ceil(1.5 uf)
+  if (U > REG_UMAX)
+    return fail(PTX_EUNSUPPORTED, "upsample_factor %d: this build supports factors up to 100", uf);
+  *U_out = U;
+  if (uf == 1 || p->reg_uf == uf) return PTX_OK;
+  const size_t N = p->ndet, count = (size_t)REG_EROWS * N;
+  if (!p->reg_E) CUDA_TRY(cudaMalloc(&p->reg_E, count * sizeof(double2)));
+  std::vector<double2> h(count, make_double2(0.0, 0.0));
+  const long long period = (long long)uf * (long long)N;
+  const long double PI2 = 6.283185307179586476925286766559L;
+  for (int j = 0; j < U; ++j)
+    for (size_t k = 0; k < N; ++k) {
+      const long long ks = k < N / 2 ? (long long)k : (long long)k - (long long)N;
+      long long q = ((long long)j * ks) % period;
+      if (q < 0) q += period;
+      const long double ang = PI2 * (long double)q / (long double)period;
+      h[(size_t)j * N + k] = make_double2((double)cosl(ang), (double)sinl(ang));
+    }
+  CUDA_TRY(cudaStreamSynchronize(st));  // a previous launch may still read the old table
+  CUDA_TRY(cudaMemcpy(p->reg_E, h.data(), count * sizeof(double2), cudaMemcpyHostToDevice));
+  p->reg_uf = uf;
+  return PTX_OK;
+}
+
+int ptx_register_translation(ptx_plan* p, const void* src, const void* target, size_t nimg,
+                             int fourier_space, int upsample_factor, double* shifts, void* stream) {
+  int rc = check_plan(p);
+  if (rc) return rc;
+  if (!src || !target || !shifts || !nimg || nimg > 0x3fffffffull)
+    return fail(PTX_EINVAL, "ptx_register_translation: bad argument");
+  cudaStream_t st = (cudaStream_t)stream;
+  int U = 0;
+  rc = reg_prepare(p, upsample_factor, &U, st);
+  if (rc) return rc;
+  PassArgs a = base_args(p);
+  a.g.T = 1;
+  a.g.S = (int)nimg;
+  a.far_in = (const float2*)src;
+  a.psi_b = (const float2*)target;
+  a.reg_E = p->reg_E;
+  a.reg_U = U;
+  a.reg_uf = upsample_factor;
+  a.reg_out = shifts;
+  return launch(p, fourier_space ? K_REG_FOURIER : K_REG_REAL, a, st);
+}
+
+int ptx_cg_position_shifts(ptx_plan* p, const void* psi_a, const void* psi_b, const void* scan,
+                           int upsample_factor, double* shifts, void* stream) {
+  int rc = check_plan(p);
+  if (rc) return rc;
+  if (!psi_a || !psi_b || !scan || !shifts) return fail(PTX_EINVAL, "ptx_cg_position_shifts: null array");
+  cudaStream_t st = (cudaStream_t)stream;
+  int U = 0;
+  rc = reg_prepare(p, upsample_factor, &U, st);
+  if (rc) return rc;
+  if (!p->ones) {
+    const size_t pp = p->nprb * p->nprb;
+    std::vector<float2> h(pp, make_float2(1.f, 0.f));
+    CUDA_TRY(cudaMalloc(&p->ones, pp * sizeof(float2)));
+    CUDA_TRY(cudaMemcpy(p->ones, h.data(), pp * sizeof(float2), cudaMemcpyHostToDevice));
+  }
+  PassArgs a = base_args(p);
+  a.g.T = 1;  // angle 0 of the chunk only, like the reference (ptycho.py:399-403)
+  a.psi = (const float2*)psi_a;
+  a.psi_b = (const float2*)psi_b;
+  a.scan = (const float2*)scan;
+  a.prb = p->ones;
+  a.reg_E = p->reg_E;
+  a.reg_U = U;
+  a.reg_uf = upsample_factor;
+  a.reg_out = shifts;
+  return launch(p, K_REG_OBJ, a, st);
 }
 
 static int vec_grid(size_t n) {

@@ -10,6 +10,10 @@
 
 namespace ptx {
 
+// position correction (ptycho_register.cuh)
+constexpr int REG_UMAX = 150;   // largest upsampled window: ceil(1.5 * 100)
+constexpr int REG_EROWS = 192;  // rows of the E table (zero beyond U: padded chunks contribute |G| = 0)
+
 // kernel parameter block, shared by every pass
 struct PassArgs {
   Geo g;
@@ -34,11 +38,16 @@ struct PassArgs {
   double* red;
   int nmodes, npairs, c0, ncand;
   int use_tma;  // object patches arrive by TMA tensor copies (tensor maps are valid)
+  // position correction (ptycho_register.cuh)
+  const double2* reg_E;  // [REG_EROWS][N] table W^(j k), W = exp(2 pi i / (uf N))
+  double* reg_out;       // [npat][2] shifts (row, col)
+  int reg_U, reg_uf;     // upsampled window size ceil(1.5 uf), upsampling factor
 };
 
 enum KernelId {
   K_FWD = 0, K_NEAR, K_ADJ_OBJ, K_ADJ_PRB, K_INT_GAUSS, K_INT_POIS,
   K_GRAD_GAUSS_OBJ, K_GRAD_GAUSS_PRB, K_GRAD_POIS_OBJ, K_GRAD_POIS_PRB, K_LS_GAUSS, K_LS_POIS,
+  K_REG_OBJ, K_REG_FOURIER, K_REG_REAL,
   K_COUNT
 };
 
@@ -46,6 +55,7 @@ struct PlanOps {
   int L, N, NT, RC;
   size_t smem_bytes;       // dynamic shared memory of the kernels that read measured data
   size_t smem_bytes_nodata;  // ... of the others (no data tile: more of the SM's SRAM stays L1)
+  size_t smem_bytes_reg;     // ... of the position-correction kernels
   size_t scratch_per_cta;  // float2
   int tw_total;            // float2
   void (*fill_tw)(float2*);

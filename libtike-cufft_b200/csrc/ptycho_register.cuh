@@ -1,0 +1,419 @@
+// Position correction: batched phase correlation with an upsampled matrix DFT around the peak.
+//
+// Replaces register_translation_batch + _upsampled_dft_batch of the reference
+// (/root/reference/src/libtike/cufft/ptycho.py:163-248) and, in its fused form, the whole
+// position-correction block of the CG loop (ptycho.py:398-403): two extra fwd() calls with an
+// all-ones probe, an element-wise product, cupy.fft.ifft2, two argmax passes and two complex128
+// einsums ([S,U,N] x [S,N,N] and [S,U,N] x [S,U,N], U = 150) -- about ten full-array kernels and
+// 0.4 GB of complex128 temporaries per 1000 patterns at 128^2 -- become ONE kernel in which a CTA
+// keeps a pattern's whole chain on chip:
+//
+//   F_a, F_b (far fields of the two objects / the two given images)     fft_tile.cuh transforms
+//   P = F_a conj(F_b)                        complex64, like the reference (ptycho.py:207)
+//   c = IFFT2(P), (y*, x*) = first argmax |c|, wrapped to signed shifts  (ptycho.py:208-219)
+//   G[jr, jc] = sum_{r,c} P[r,c] W^((jr-off_r) k_r + (jc-off_c) k_c),  W = exp(2 pi i / (uf N)),
+//       off = dftshift - shift * uf, k = signed frequency index          (ptycho.py:221-233, 163-190)
+//   (jr*, jc*) = first argmax |G|;  shift += (j* - dftshift) / uf        (ptycho.py:234-240)
+//
+// The upsampled DFT is evaluated exactly as the reference does it -- as two matrix products in
+// float64 -- because near the peak neighbouring samples of |G| differ by far less than float32
+// resolution.  Since `off` is an integer, W^((j-off) k) = E[j][k] * ph[k] with a PATTERN-INDEPENDENT
+// table E[j][k] = W^(j k) (one [U, N] complex128 table per plan and upsampling factor, L2 resident)
+// and two per-pattern phase vectors ph_r, ph_c (N sincospi each).  Per jc-chunk of JC columns:
+//   stage 1   T[jc][r]  = ph_r[r] * sum_c E[jc][c] (P[r][c] ph_c[c])     register tile 2 x 4 / thread
+//   stage 2   G[jr][jc] = sum_r E[jr][r] T[jc][r]                        register tile TJR x TJC / thread
+// with A/B tiles staged through shared memory (pitch KCH+1 complex128 = conflict-free 128-bit
+// loads for lanes on consecutive rows) and T kept in shared memory: the float64 pipe (DFMA) is the
+// roof, 4 DFMA per complex multiply-add, (U' N^2 + U'^2 N) of them per pattern (U' = U rounded up).
+#pragma once
+
+#include "ptycho_passes.cuh"
+
+namespace ptx {
+
+template <class P>
+struct RegCfg;  // JC: window columns per chunk; KCH: contraction chunk; TJR x TJC: stage-2 thread tile
+template <>
+struct RegCfg<Plan<6>> {
+  static constexpr int JC = 32, KCH = 16, TJR = 5, TJC = 2;
+};
+template <>
+struct RegCfg<Plan<7>> {
+  static constexpr int JC = 32, KCH = 16, TJR = 5, TJC = 2;
+};
+template <>
+struct RegCfg<Plan<8>> {
+  static constexpr int JC = 16, KCH = 8, TJR = 5, TJC = 1;
+};
+template <>
+struct RegCfg<Plan<9>> {
+  static constexpr int JC = 8, KCH = 4, TJR = 3, TJC = 1;
+};
+
+template <class P>
+struct RegGeom {
+  using C = RegCfg<P>;
+  static constexpr int N = P::N, NT = P::NT, NW = NT / 32;
+  static constexpr int JC = C::JC, KCH = C::KCH, TJR = C::TJR, TJC = C::TJC;
+  static constexpr int KP = KCH + 1;  // tile pitch in complex128
+  // stage 1: a warp is 4 (jc) x 8 (r) lanes, 2 x 4 outputs per lane -> 8 jc x 32 r per warp
+  static constexpr int W1J = JC / 8, W1R = NW / W1J, RCH = 32 * W1R;
+  // stage 2: a warp is 8 (jc) x 4 (jr) lanes, TJC x TJR outputs per lane
+  static constexpr int W2C = JC / (8 * TJC), W2R = NW / W2C, JRCH = 4 * TJR * W2R;
+  static constexpr int TP = N + 1;  // pitch of T
+  // shared layout (complex128 units)
+  static constexpr int SZ_A = JC * KP, SZ_B = RCH * KP, SZ_A2 = JRCH * KP;
+  static constexpr int SZ_AB = (SZ_A + SZ_B) > SZ_A2 ? (SZ_A + SZ_B) : SZ_A2;
+  static constexpr int OFF_T = SZ_AB, OFF_PH = OFF_T + JC * TP, TOTAL = OFF_PH + 2 * N;
+  static constexpr size_t BYTES = (size_t)TOTAL * 16;
+  // the GEMM region reuses the FFT tile when it fits, else it follows the mbarriers
+  static constexpr bool IN_TILE = BYTES <= Smem<P>::OFF_TW;
+  static constexpr size_t OFF = IN_TILE ? 0 : Smem<P>::OFF_DBUF;
+  static constexpr size_t SMEM = IN_TILE ? Smem<P>::BYTES_NODATA : Smem<P>::OFF_DBUF + BYTES;
+  static_assert(W1J >= 1 && W1R >= 1 && W1J * W1R == NW, "stage-1 warp grid");
+  static_assert(W2C >= 1 && W2R >= 1 && W2C * W2R == NW, "stage-2 warp grid");
+  static_assert(N % RCH == 0 && N % KCH == 0, "chunking");
+  static_assert(REG_EROWS % JC == 0 && REG_EROWS >= ((REG_UMAX + JRCH - 1) / JRCH) * JRCH, "E rows");
+};
+
+struct Best {
+  float v;
+  int i;
+};
+__device__ __forceinline__ void best_take(Best& b, float v, int i) {
+  if (v > b.v || (v == b.v && i < b.i)) {
+    b.v = v;
+    b.i = i;
+  }
+}
+struct BestD {
+  double v;
+  int i;
+};
+__device__ __forceinline__ void bestd_take(BestD& b, double v, int i) {
+  if (v > b.v || (v == b.v && i < b.i)) {
+    b.v = v;
+    b.i = i;
+  }
+}
+// first-occurrence argmax over the CTA (numpy / cupy argmax: the smallest index among equal maxima)
+template <int NW>
+__device__ __forceinline__ int block_argmax(BestD b, double* red, int tid) {
+#pragma unroll
+  for (int off = 16; off > 0; off >>= 1) {
+    const double ov = __shfl_down_sync(0xffffffffu, b.v, off);
+    const int oi = __shfl_down_sync(0xffffffffu, b.i, off);
+    bestd_take(b, ov, oi);
+  }
+  int* ri = reinterpret_cast<int*>(red + NW);
+  __syncthreads();
+  if ((tid & 31) == 0) {
+    red[tid >> 5] = b.v;
+    ri[tid >> 5] = b.i;
+  }
+  __syncthreads();
+  BestD r;
+  r.v = red[0];
+  r.i = ri[0];
+  for (int w = 1; w < NW; ++w) bestd_take(r, red[w], ri[w]);
+  __syncthreads();
+  return r.i;
+}
+
+__device__ __forceinline__ void zfma(double2& acc, const double2 a, const double2 b) {
+  acc.x = fma(a.x, b.x, acc.x);
+  acc.x = fma(-a.y, b.y, acc.x);
+  acc.y = fma(a.x, b.y, acc.y);
+  acc.y = fma(a.y, b.x, acc.y);
+}
+
+// The matrix-DFT refinement of one pattern.  praw: [N][N] complex64 image product in natural
+// frequency order (this CTA's scratch); (sy, sx): whole-pixel shifts.  Returns the flat index
+// jr * U + jc of the first maximum of |G|.
+template <class P>
+__device__ __forceinline__ int register_refine(const float2* __restrict__ praw,
+                                               const double2* __restrict__ E, double2* sm,
+                                               double* red, int tid, int sy, int sx, int U, int uf,
+                                               int dftshift) {
+  using G = RegGeom<P>;
+  constexpr int N = G::N, NT = G::NT, KP = G::KP, KCH = G::KCH, JC = G::JC;
+  double2* As = sm;
+  double2* Bs = sm + G::SZ_A;
+  double2* A2s = sm;
+  double2* Ts = sm + G::OFF_T;
+  double2* phr = sm + G::OFF_PH;
+  double2* phc = phr + N;
+  const int lane = tid & 31, warp = tid >> 5;
+  // per-pattern phase vectors: ph[k] = W^(-off k_signed), -off = shift * uf - dftshift
+  const int period = uf * N;
+  for (int k = tid; k < 2 * N; k += NT) {
+    const int kk = k < N ? k : k - N;
+    const int ks = kk < N / 2 ? kk : kk - N;
+    const int m = (k < N ? sy : sx) * uf - dftshift;
+    long long q = ((long long)m * ks) % period;
+    if (q < 0) q += period;
+    double s, c;
+    sincospi(2.0 * (double)q / (double)period, &s, &c);
+    (k < N ? phr : phc)[kk] = make_double2(c, s);
+  }
+  // stage-1 thread coordinates
+  const int tjl = lane & 3, trl = lane >> 2;
+  const int w1j = warp % G::W1J, w1r = warp / G::W1J;
+  // stage-2 thread coordinates
+  const int cl = lane & 7, rl = lane >> 3;
+  const int w2c = warp % G::W2C, w2r = warp / G::W2C;
+  BestD best;
+  best.v = -1.0;
+  best.i = 0;
+  for (int jc0 = 0; jc0 < U; jc0 += JC) {
+    // ---------------- stage 1: T[jc][r] = ph_r[r] sum_c E[jc0+jc][c] P[r][c] ph_c[c]
+    for (int r0 = 0; r0 < N; r0 += G::RCH) {
+      double2 acc[2][4];
+#pragma unroll
+      for (int i = 0; i < 2; ++i)
+#pragma unroll
+        for (int q = 0; q < 4; ++q) acc[i][q] = make_double2(0.0, 0.0);
+      for (int k0 = 0; k0 < N; k0 += KCH) {
+        __syncthreads();  // the previous tiles (and, first time round, the phase vectors) are settled
+        for (int t = tid; t < JC * KCH; t += NT) {
+          const int j = t / KCH, kk = t % KCH;
+          As[j * KP + kk] = __ldg(E + (size_t)(jc0 + j) * N + k0 + kk);
+        }
+        for (int t = tid; t < G::RCH * KCH; t += NT) {
+          const int r = t / KCH, kk = t % KCH;
+          const float2 pv = __ldcg(praw + (size_t)(r0 + r) * N + k0 + kk);
+          const double2 ph = phc[k0 + kk];
+          Bs[r * KP + kk] = make_double2((double)pv.x * ph.x - (double)pv.y * ph.y,
+                                         (double)pv.x * ph.y + (double)pv.y * ph.x);
+        }
+        __syncthreads();
+        const double2* ap = As + (tjl + 8 * w1j) * KP;
+        const double2* bp = Bs + (trl + 32 * w1r) * KP;
+#pragma unroll 4
+        for (int kk = 0; kk < KCH; ++kk) {
+          const double2 a0 = ap[kk], a1 = ap[4 * KP + kk];
+          double2 b[4];
+#pragma unroll
+          for (int q = 0; q < 4; ++q) b[q] = bp[8 * q * KP + kk];
+#pragma unroll
+          for (int q = 0; q < 4; ++q) {
+            zfma(acc[0][q], a0, b[q]);
+            zfma(acc[1][q], a1, b[q]);
+          }
+        }
+      }
+#pragma unroll
+      for (int i = 0; i < 2; ++i)
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+          const int j = tjl + 4 * i + 8 * w1j, r = r0 + trl + 8 * q + 32 * w1r;
+          const double2 ph = phr[r], a = acc[i][q];
+          Ts[j * G::TP + r] = make_double2(a.x * ph.x - a.y * ph.y, a.x * ph.y + a.y * ph.x);
+        }
+    }
+    // ---------------- stage 2: G[jr][jc0+jc] = sum_r E[jr][r] T[jc][r]
+    for (int jr0 = 0; jr0 < U; jr0 += G::JRCH) {
+      double2 acc[G::TJR][G::TJC];
+#pragma unroll
+      for (int i = 0; i < G::TJR; ++i)
+#pragma unroll
+        for (int q = 0; q < G::TJC; ++q) acc[i][q] = make_double2(0.0, 0.0);
+      for (int k0 = 0; k0 < N; k0 += KCH) {
+        __syncthreads();  // stage-1 tiles / previous A2 tile consumed, T complete
+        for (int t = tid; t < G::JRCH * KCH; t += NT) {
+          const int j = t / KCH, kk = t % KCH;
+          A2s[j * KP + kk] = __ldg(E + (size_t)(jr0 + j) * N + k0 + kk);
+        }
+        __syncthreads();
+        const double2* ap = A2s + (rl + 4 * G::TJR * w2r) * KP;
+        const double2* bp = Ts + (cl + 8 * G::TJC * w2c) * G::TP + k0;
+#pragma unroll 4
+        for (int kk = 0; kk < KCH; ++kk) {
+          double2 b[G::TJC];
+#pragma unroll
+          for (int q = 0; q < G::TJC; ++q) b[q] = bp[8 * q * G::TP + kk];
+#pragma unroll
+          for (int i = 0; i < G::TJR; ++i) {
+            const double2 a = ap[4 * i * KP + kk];
+#pragma unroll
+            for (int q = 0; q < G::TJC; ++q) zfma(acc[i][q], a, b[q]);
+          }
+        }
+      }
+#pragma unroll
+      for (int i = 0; i < G::TJR; ++i)
+#pragma unroll
+        for (int q = 0; q < G::TJC; ++q) {
+          const int jr = jr0 + rl + 4 * i + 4 * G::TJR * w2r;
+          const int jc = jc0 + cl + 8 * q + 8 * G::TJC * w2c;
+          if (jr < U && jc < U) {
+            const double2 a = acc[i][q];
+            bestd_take(best, a.x * a.x + a.y * a.y, jr * U + jc);
+          }
+        }
+    }
+  }
+  return block_argmax<G::NW>(best, red, tid);
+}
+
+// MODE 0: far fields of two OBJECTS under an all-ones probe at the scan positions (ptycho.py:398-401)
+// MODE 1: src / target given in Fourier space [S,N,N] (register_translation_batch(space='fourier'))
+// MODE 2: src / target given in real space [S,N,N]    (space='real': fft2 of both first)
+template <class P, int MODE>
+__global__ void __launch_bounds__(P::NT) k_register(const PassArgs a,
+                                                    const __grid_constant__ CUtensorMap tm_a,
+                                                    const __grid_constant__ CUtensorMap tm_b) {
+  extern __shared__ __align__(128) unsigned char smem_raw[];
+  using G = RegGeom<P>;
+  Cta<P> c;
+  cta_setup<P>(c, smem_raw, a);
+  const Geo g = a.g;
+  constexpr size_t NN = (size_t)P::N * P::N;
+  double2* gemm = reinterpret_cast<double2*>(smem_raw + G::OFF);
+  float2* praw = reinterpret_cast<float2*>(c.accp);  // [N][N] complex64, natural frequency order
+  const int npat = g.T * g.S;
+  const int U = a.reg_U, uf = a.reg_uf, dftshift = U / 2;
+  for (int pat = blockIdx.x; pat < npat; pat += gridDim.x) {
+    const int t = pat / g.S;
+    Pat p;
+    p.skip = false;
+    if (MODE == 0) p = make_pat(a.scan, pat, g);
+    double* out = a.reg_out + 2 * (size_t)pat;
+    if (p.skip) {  // both far fields are identically 0: every argmax lands on index 0 (ptycho.py:210, 236)
+      if (c.tid == 0) {
+        const double s = uf > 1 ? -(double)dftshift / (double)uf : 0.0;
+        out[0] = s;
+        out[1] = s;
+      }
+      continue;
+    }
+    const float2* src = MODE == 0 ? a.psi + (size_t)t * g.nz * g.n : a.far_in + (size_t)pat * NN;
+    const float2* tgt = MODE == 0 ? a.psi_b + (size_t)t * g.nz * g.n : a.psi_b + (size_t)pat * NN;
+    Best bst;
+    bst.v = -1.f;
+    bst.i = 0;
+    // v holds the target's spectrum; src_at(e) fetches the source's
+    auto product = [&](int k1, float2(&v)[P::E], auto src_at) {
+#pragma unroll
+      for (int e = 0; e < P::E; ++e) {
+        v[e] = cmulc(src_at(e), v[e]);  // src * conj(target), complex64 (ptycho.py:207)
+        __stcg(praw + spec_index<P>(c, k1, e), v[e]);
+      }
+    };
+    auto peak = [&](int cb, float2(&v)[P::E]) {
+#pragma unroll
+      for (int e = 0; e < P::E; ++e) {
+        int y, x;
+        nat_coord<P>(c, cb, e, y, x);
+        best_take(bst, v[e].x * v[e].x + v[e].y * v[e].y, y * P::N + x);
+      }
+    };
+    if (MODE == 1) {
+      inverse_pass<P>(
+          c,
+          [&](int k1, float2(&v)[P::E]) {
+#pragma unroll
+            for (int e = 0; e < P::E; ++e) v[e] = __ldg(tgt + spec_index<P>(c, k1, e));
+            product(k1, v, [&](int e) { return __ldg(src + spec_index<P>(c, k1, e)); });
+          },
+          peak);
+    } else {
+      auto load_nat = [&](const float2* img, const float2* ones, int cb, float2(&v)[P::E]) {
+        if (MODE == 0) {
+          gather_nat<P>(v, c, cb, img, ones, g, p);
+        } else {
+#pragma unroll
+          for (int e = 0; e < P::E; ++e) {
+            int y, x;
+            nat_coord<P>(c, cb, e, y, x);
+            v[e] = __ldg(img + y * P::N + x);
+          }
+        }
+      };
+      spectrum_pass<P>(
+          c, false, [&](int cb, float2(&v)[P::E]) { load_nat(src, a.prb, cb, v); },
+          [&](int k1, float2(&v)[P::E]) {
+            float2* st = c.stash + (size_t)k1 * P::E * P::NT + c.tid;
+#pragma unroll
+            for (int e = 0; e < P::E; ++e) st[e * P::NT] = v[e];
+          },
+          [&](int) {});
+      fused_pass<P>(
+          c, [&](int cb, float2(&v)[P::E]) { load_nat(tgt, a.prb, cb, v); },
+          [&](int k1, float2(&v)[P::E]) {
+            const float2* st = c.stash + (size_t)k1 * P::E * P::NT + c.tid;
+            product(k1, v, [&](int e) { return st[e * P::NT]; });
+          },
+          [&](int) {}, peak);
+    }
+    BestD bd;
+    bd.v = (double)bst.v;
+    bd.i = bst.i;
+    const int imax = block_argmax<G::NW>(bd, c.red, c.tid);  // its barriers also publish praw
+    int sy = imax / P::N, sx = imax % P::N;
+    if (sy > P::N / 2) sy -= P::N;  // ptycho.py:213-219: strictly beyond the midpoint wraps
+    if (sx > P::N / 2) sx -= P::N;
+    double oy = (double)sy, ox = (double)sx;
+    if (uf > 1) {
+      const int j = register_refine<P>(praw, a.reg_E, gemm, c.red, c.tid, sy, sx, U, uf, dftshift);
+      oy += (double)(j / U - dftshift) / (double)uf;
+      ox += (double)(j % U - dftshift) / (double)uf;
+    }
+    if (c.tid == 0) {
+      out[0] = oy;
+      out[1] = ox;
+    }
+    __syncthreads();  // the GEMM region (= the FFT tile) is free again
+  }
+}
+
+// ------------------------------------------------------------------------------------------
+// the family's dispatch table
+// ------------------------------------------------------------------------------------------
+template <class P>
+static void fill_tw_host(float2* tw) {
+  fill_twiddles<P>(tw);
+}
+
+template <class P>
+const PlanOps* make_ops() {
+  static PlanOps ops;
+  static bool init = false;
+  if (!init) {
+    ops.L = P::L;
+    ops.N = P::N;
+    ops.NT = P::NT;
+    ops.RC = P::RC;
+    ops.smem_bytes = Smem<P>::BYTES;
+    ops.smem_bytes_nodata = Smem<P>::BYTES_NODATA;
+    ops.smem_bytes_reg = RegGeom<P>::SMEM;
+    ops.scratch_per_cta = Scratch<P>::TOTAL;
+    ops.tw_total = TwLayout<P>::TOTAL;
+    ops.fill_tw = fill_tw_host<P>;
+    ops.patch_w = Patch<P>::TMA ? Patch<P>::W : 0;
+    ops.patch_h = Patch<P>::TMA ? Patch<P>::H : 0;
+#define PTX_SET(id, ...)                                   \
+  ops.kernels[id] = (const void*)(void (*)(const PassArgs, const CUtensorMap, const CUtensorMap))(__VA_ARGS__); \
+  ops.names[id] = #__VA_ARGS__;
+    PTX_SET(K_FWD, k_fwd<P>)
+    PTX_SET(K_NEAR, k_nearplane<P>)
+    PTX_SET(K_ADJ_OBJ, k_adj<P, 0>)
+    PTX_SET(K_ADJ_PRB, k_adj<P, 1>)
+    PTX_SET(K_INT_GAUSS, k_intensity<P, 0>)
+    PTX_SET(K_INT_POIS, k_intensity<P, 1>)
+    PTX_SET(K_GRAD_GAUSS_OBJ, k_grad<P, 0, 0>)
+    PTX_SET(K_GRAD_GAUSS_PRB, k_grad<P, 0, 1>)
+    PTX_SET(K_GRAD_POIS_OBJ, k_grad<P, 1, 0>)
+    PTX_SET(K_GRAD_POIS_PRB, k_grad<P, 1, 1>)
+    PTX_SET(K_LS_GAUSS, k_linesearch<P, 0>)
+    PTX_SET(K_LS_POIS, k_linesearch<P, 1>)
+    PTX_SET(K_REG_OBJ, k_register<P, 0>)
+    PTX_SET(K_REG_FOURIER, k_register<P, 1>)
+    PTX_SET(K_REG_REAL, k_register<P, 2>)
+#undef PTX_SET
+    init = true;
+  }
+  return &ops;
+}
+
+}  // namespace ptx

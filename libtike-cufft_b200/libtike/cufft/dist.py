@@ -89,6 +89,10 @@ class ScalarComm(object):
     def world(self):
         return dist.get_world_size(self.group) if dist.is_initialized() else 1
 
+    @property
+    def rank(self):
+        return dist.get_rank(self.group) if dist.is_initialized() else 0
+
     def sum_(self, t):
         if self.world > 1:
             dist.all_reduce(t, op=dist.ReduceOp.SUM, group=self.group)

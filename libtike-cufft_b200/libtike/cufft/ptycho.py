@@ -21,9 +21,10 @@ Documented deviations from the reference (see DESIGN.md "Quirks"):
   Q1  model='poisson' object gradient: the reference raises UnboundLocalError
       (ptycho.py:357-363 reads `fpsi` before assignment); the evident missing
       line `fpsi = self.fwd(psi, scan, probe[:, k])` is supplied.
-  Q5  the position-correction block (ptycho.py:398-403) runs only when the
-      solver attribute `position_correction` is True (default False; it is a
-      "next" row).
+  Q5  the position-correction block (ptycho.py:398-403), unconditional in the
+      reference, is one fused kernel (ptx_cg_position_shifts) and can be switched
+      off with the solver attribute `position_correction` (default True = the
+      reference's behaviour; False = the primary CG parity configuration).
   Q9  `_batch` chunks by ptheta (identical at ptheta = 1, the only value the
       reference's helper is valid for).
 """
@@ -35,7 +36,7 @@ import torch
 
 from libtike.cufft.ptychofft import ptychofft, lib, check, current_stream, PtxError  # noqa: F401
 
-__all__ = ["PtychoCuFFT", "CGPtychoSolver", "line_search_gammas"]
+__all__ = ["PtychoCuFFT", "CGPtychoSolver", "register_translation_batch", "line_search_gammas"]
 
 MODELS = {"gaussian": 0, "poisson": 1}
 
@@ -250,6 +251,44 @@ class PtychoCuFFT(ptychofft):
         return {"psi": psi, "probe": probe}
 
 
+_REG_PLANS = {}
+
+
+def register_translation_batch(src_image, target_image, upsample_factor=1, space="real"):
+    """Batched sub-pixel image registration by phase correlation (reference: ptycho.py:192-248).
+
+    src_image, target_image : [S, N, N] complex64 device arrays (N in {64, 128, 256, 512});
+    space='fourier' means they already are Fourier transforms.  Returns the float64 shifts [S, 2]
+    (row, col) as a device tensor, refined to 1/upsample_factor of a pixel by the reference's
+    upsampled matrix DFT (ptycho.py:163-190) -- one fused kernel instead of two cupy.fft calls, two
+    argmax passes and two complex128 einsums.  Like the reference, a batch of ONE image comes back
+    as zeros (its trailing `shape[dim] == 1` loop indexes the batch axis, ptycho.py:243-245).
+    """
+    src = _dev_tensor(src_image)
+    tgt = _dev_tensor(target_image)
+    if space.lower() not in ("fourier", "real"):
+        raise ValueError("space must be 'real' or 'fourier'")
+    if src.dtype != torch.complex64 or tgt.dtype != torch.complex64:
+        raise TypeError("register_translation_batch needs complex64 images")
+    if src.ndim != 3 or src.shape != tgt.shape or src.shape[1] != src.shape[2]:
+        raise ValueError("register_translation_batch needs two [S, N, N] stacks of equal shape")
+    if int(upsample_factor) != upsample_factor:
+        raise ValueError("upsample_factor must be an integer")
+    src, tgt = src.contiguous(), tgt.contiguous()
+    S, N = src.shape[0], src.shape[2]
+    key = (N, src.device.index)
+    plan = _REG_PLANS.get(key)
+    if plan is None:  # a plan only carries twiddles and per-CTA scratch; object size is irrelevant here
+        plan = _REG_PLANS[key] = ptychofft(1, N + 1, N + 1, 4096, N, N)
+    shifts = torch.empty((S, 2), dtype=torch.float64, device=src.device)
+    check(lib.ptx_register_translation(plan._h, _ptr(src), _ptr(tgt), S,
+                                       1 if space.lower() == "fourier" else 0,
+                                       int(upsample_factor), _ptr(shifts), current_stream()))
+    if S == 1:
+        shifts[0] = 0
+    return shifts
+
+
 def line_search_gammas(c0, ncand):
     return [2.0 ** -(c0 + c) for c in range(ncand)]
 
@@ -257,8 +296,11 @@ def line_search_gammas(c0, ncand):
 class CGPtychoSolver(PtychoCuFFT):
     """Solve the ptychography problem using conjugate gradient (reference: ptycho.py:250-488)."""
 
-    #: Q5 -- execute the reference's position-correction block (ptycho.py:398-403)
-    position_correction = False
+    #: Q5 -- execute the reference's position-correction block (ptycho.py:398-403); the reference
+    #: has no switch (always on).  False = the primary CG parity configuration.
+    position_correction = True
+    #: upsampling factor of the position correction (ptycho.py:401)
+    position_upsample = 100
     #: step candidates evaluated per fused line-search pass
     ls_candidates = 4
     #: diagnostics hook used by the parity tests: a list of raw line-search results, consumed in call
@@ -480,6 +522,7 @@ class CGPtychoSolver(PtychoCuFFT):
         gammaprb = 0
         self.history = []  # (iteration, step size object, step size probe) -- diagnostics only
         self.ls_log = []   # (first candidate exponent, [f(0), f(2^-c0), ...]) per fused pass
+        self.shift_log = []  # device [S,2] float64 shifts of every position-correction step
         for i in range(piter):
             # 1) object retrieval subproblem with fixed probes (ptycho.py:327-345).  a, b, the probe
             # rescaling and the gradient scalars stay on the device: no host round trip here
@@ -505,10 +548,24 @@ class CGPtychoSolver(PtychoCuFFT):
             gammapsi = 0.5 * self._line_search(psi, probe, M, 0, dpsi, probe, M, 0, M, scan, data,
                                                None, mdl)
             if self.position_correction and i > 0:
-                raise NotImplementedError(
-                    "position correction (ptycho.py:398-403) is a 'next' row and not built yet")
-            # update psi (ptycho.py:405)
-            self._axpy(psi, dpsi, gammapsi)
+                # position correction (ptycho.py:398-403): register the all-ones-probe far fields of
+                # psi and psi + gamma dpsi for angle 0 and move its scan positions -- the caller's
+                # scan array is updated in place, like the reference's
+                psi_new = psi.clone()
+                self._axpy(psi_new, dpsi, gammapsi)
+                if self.comm is None or self.comm.rank == 0:  # angle 0 of the run lives on rank 0
+                    shifts = torch.empty((S, 2), dtype=torch.float64, device=dev)
+                    check(lib.ptx_cg_position_shifts(self._h, _ptr(psi), _ptr(psi_new), _ptr(scan),
+                                                     int(self.position_upsample), _ptr(shifts),
+                                                     current_stream()))
+                    if S == 1:  # the reference's shape[dim] == 1 loop (ptycho.py:243-245)
+                        shifts[0] = 0
+                    self.shift_log.append(shifts)
+                    scan[0] = (scan[0].double() + shifts).float()  # float32 += float64, as CuPy casts
+                psi = psi_new
+            else:
+                # update psi (ptycho.py:405)
+                self._axpy(psi, dpsi, gammapsi)
 
             if recover_prb:
                 for m in range(M):

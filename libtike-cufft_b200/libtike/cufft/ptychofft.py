@@ -39,6 +39,8 @@ SYMBOLS = [
     ("ptx_cg_grad", _i, [_vp, _i, _vp, _vp, _vp, _i, _i, _fp, _fp, _fp, _i, _vp, _sz, _vp]),
     ("ptx_cg_linesearch", _i, [_vp, _vp, _vp, _i, _i, _vp, _vp, _i, _i, _i, _vp, _fp, _fp, _i, _i,
                                _i, _dp, _vp]),
+    ("ptx_register_translation", _i, [_vp, _vp, _vp, _sz, _i, _i, _dp, _vp]),
+    ("ptx_cg_position_shifts", _i, [_vp, _vp, _vp, _vp, _i, _dp, _vp]),
     ("ptx_vec_dai_yuan_reduce", _i, [_vp, _vp, _vp, _sz, _dp, _vp]),
     ("ptx_vec_dai_yuan_update", _i, [_vp, _vp, _vp, _sz, _dp, _i, _vp]),
     ("ptx_vec_axpy", _i, [_vp, _vp, _sz, _fp, _vp]),

@@ -19,6 +19,7 @@ What follows what (paths relative to /root/reference):
   fwd ............................. src/cuda/kernels.cu:95-107 + src/cuda/ptychofft.cu:60-73
   adj (object, flg 0) ............. src/cuda/ptychofft.cu:76-88 + src/cuda/kernels.cu:69-81
   adj_probe (flg 1) ............... src/cuda/ptychofft.cu:76-88 + src/cuda/kernels.cu:82-94
+  register_translation_batch ...... src/libtike/cufft/ptycho.py:163-248
   line_search_sqr ................. src/libtike/cufft/ptycho.py:253-281
   cg_run .......................... src/libtike/cufft/ptycho.py:283-488
 cuFFT (closed source, CUDA toolkit 12.9 -> cuFFT 11.4.1; call sites
@@ -178,6 +179,74 @@ def adj_probe(g, scan, psi, nprb, workers=-1):
 
 
 # ----------------------------------------------------------------------------
+# Position correction (ptycho.py:163-248), "next" row f1 of SURVEY.md section 8.
+# ----------------------------------------------------------------------------
+
+def _upsampled_dft_batch(data, ups, upsample_factor=1, axis_offsets=None):
+    """ptycho.py:163-190 -- matrix-multiply DFT of an `ups` x `ups` window of the upsampled inverse
+    transform, complex128 (float64 kernels times complex64 data).
+
+    data [S,N,N]; axis_offsets [S,2] (row, col).  rec[i, jr, jc] =
+      sum_{r,c} exp(-2 pi i (jr - off_r) f[r]) exp(-2 pi i (jc - off_c) f[c]) data[i, r, c],
+    f = fftfreq(N, upsample_factor).  Both kernels use data.shape[2] (the reference's square-frame
+    assumption, ptycho.py:182, 185).
+    """
+    im2pi = 1j * 2 * np.pi
+    ups = int(ups)
+    S = data.shape[0]
+    freq = np.fft.fftfreq(data.shape[2], upsample_factor)
+    kernel = (np.tile(np.arange(ups), (S, 1)) - axis_offsets[:, 1:2])[:, :, None] * freq
+    kernel = np.exp(-im2pi * kernel)
+    tdata = np.einsum('ijk,ipk->ijp', kernel, data)
+    kernel = (np.tile(np.arange(ups), (S, 1)) - axis_offsets[:, 0:1])[:, :, None] * freq
+    kernel = np.exp(-im2pi * kernel)
+    return np.einsum('ijk,ipk->ijp', kernel, tdata)
+
+
+def register_translation_batch(src_image, target_image, upsample_factor=1, space="real"):
+    """ptycho.py:192-248 -- batched phase correlation with an upsampled matrix DFT around the
+    whole-pixel peak.  Returns float64 shifts [S,2] (row, col).  Statement by statement, including
+    the trailing `shape[dim] == 1` loop, which for a batch of ONE image zeroes that image's shifts
+    (it indexes the batch axis; ptycho.py:243-245)."""
+    if space.lower() == 'fourier':
+        src_freq = src_image
+        target_freq = target_image
+    elif space.lower() == 'real':
+        src_freq = sfft.fft2(src_image, axes=(-2, -1))
+        target_freq = sfft.fft2(target_image, axes=(-2, -1))
+    shape = src_freq.shape
+    image_product = src_freq * target_freq.conj()
+    cross_correlation = sfft.ifft2(image_product, axes=(-2, -1))
+    A = np.abs(cross_correlation)
+    maxima = A.reshape(A.shape[0], -1).argmax(1)
+    maxima = np.column_stack(np.unravel_index(maxima, A[0, :, :].shape))
+    midpoints = np.array([np.fix(axis_size / 2) for axis_size in shape[1:]])
+    shifts = np.array(maxima, dtype=np.float64)
+    ids = np.where(shifts[:, 0] > midpoints[0])
+    shifts[ids[0], 0] -= shape[1]
+    ids = np.where(shifts[:, 1] > midpoints[1])
+    shifts[ids[0], 1] -= shape[2]
+    if upsample_factor > 1:
+        shifts = np.round(shifts * upsample_factor) / upsample_factor
+        upsampled_region_size = np.ceil(upsample_factor * 1.5)
+        dftshift = np.fix(upsampled_region_size / 2.0)
+        normalization = (src_freq[0].size * upsample_factor ** 2)
+        sample_region_offset = dftshift - shifts * upsample_factor
+        cross_correlation = _upsampled_dft_batch(image_product.conj(), upsampled_region_size,
+                                                 upsample_factor, sample_region_offset).conj()
+        cross_correlation /= normalization
+        A = np.abs(cross_correlation)
+        maxima = A.reshape(A.shape[0], -1).argmax(1)
+        maxima = np.column_stack(np.unravel_index(maxima, A[0, :, :].shape))
+        maxima = np.array(maxima, dtype=np.float64) - dftshift
+        shifts = shifts + maxima / upsample_factor
+    for dim in range(src_freq.ndim):
+        if shape[dim] == 1:
+            shifts[dim] = 0
+    return shifts
+
+
+# ----------------------------------------------------------------------------
 # CG solver (ptycho.py:250-488), float32 arithmetic like CuPy's.
 # ----------------------------------------------------------------------------
 
@@ -202,14 +271,16 @@ def line_search_sqr(f, p1, p2, p3, step_length=1, step_shrink=0.5, forced=None):
 
 
 def cg_run(data, psi, scan, probe, piter, model="gaussian", recover_prb=False,
-           ndet=None, verbose=False, history=None, forced_steps=None):
+           ndet=None, verbose=False, history=None, forced_steps=None, position_correction=False,
+           shift_log=None):
     """Statement-by-statement restatement of CGPtychoSolver.run (ptycho.py:283-488).
 
     Deviations, all deliberate and documented in DESIGN.md:
       * Q1: the Poisson object branch reads `fpsi` before assignment
         (ptycho.py:357-363); the evident missing line `fpsi = fwd(...)` is added.
-      * Q5: the position-correction block (ptycho.py:398-403) is NOT executed
-        (primary parity configuration; it is a "next" row).
+      * Q5: the position-correction block (ptycho.py:398-403), unconditional in the reference,
+        is behind `position_correction` (off = the primary parity configuration).  It mutates
+        the caller's `scan` (angle 0 only), like the reference.
       * Q7: the dead `sfpsi` recompute (ptycho.py:476-480) is skipped.
     data [T,S,N,N] f32, psi [T,nz,n] c64, scan [T,S,2] f32, probe [T,M,P,P] c64.
     """
@@ -267,6 +338,14 @@ def cg_run(data, psi, scan, probe, piter, model="gaussian", recover_prb=False,
             p2 += np.abs(tmp2) ** 2
             p3 += 2 * (tmp1.real * tmp2.real + tmp1.imag * tmp2.imag)
         gammapsi = 0.5 * line_search_sqr(minf, p1, p2, p3, forced=forced_steps)
+        if position_correction and i > 0:  # ptycho.py:398-403
+            ones = probe[:, 0] * 0 + 1
+            tmp1 = _fwd(psi, ones)[0]
+            tmp2 = _fwd((psi + F32(gammapsi) * dpsi).astype(C64), ones)[0]
+            shifts = register_translation_batch(tmp1, tmp2, upsample_factor=100, space='fourier')
+            if shift_log is not None:
+                shift_log.append(shifts.copy())
+            scan[0, :] += shifts
         psi = (psi + F32(gammapsi) * dpsi).astype(C64)
 
         if recover_prb:

@@ -12,8 +12,10 @@ __graft_entry__.smoke() and bench.py's reference arm may import this module.
   reference's Python layer cannot be imported -- SURVEY.md section 8c).  Deviations:
     Q1  the missing `fpsi = self.fwd(...)` line of the Poisson object branch
         (ptycho.py:357-363) is added (the reference raises UnboundLocalError);
-    Q5  the position-correction block (ptycho.py:398-403) is behind
-        `position_correction` (default False, the primary parity configuration);
+    Q5  the position-correction block (ptycho.py:398-403), unconditional in the reference, is
+        behind `position_correction` (False = the primary parity configuration);
+        `register_translation_batch` / `_upsampled_dft_batch` (ptycho.py:163-248) are restated
+        with cp -> torch (cuFFT + complex128 einsum, like CuPy);
     Q7  the dead `sfpsi` recompute (ptycho.py:476-480) is skipped;
     Q10 `probe[:, k]` views are made contiguous before their pointer is taken (the
         reference passes the view's base pointer, which is only right for ptheta = 1).
@@ -136,6 +138,62 @@ class RefPtychoFFT(object):
         return self._batch(self.adj_probe, probe, farplane, scan, psi)
 
 
+def _upsampled_dft_batch(data, ups, upsample_factor=1, axis_offsets=None):
+    """ptycho.py:163-190 with cp -> torch; the kernels are float64 -> complex128 and CuPy's einsum
+    promotes the complex64 data to complex128, which torch needs spelled out."""
+    ups = int(ups)
+    S = data.shape[0]
+    dev = data.device
+    freq = torch.fft.fftfreq(data.shape[2], upsample_factor, dtype=torch.float64, device=dev)
+    tdata = data.to(torch.complex128)
+    ar = torch.arange(ups, dtype=torch.float64, device=dev).repeat(S, 1)
+    kernel = (ar - axis_offsets[:, 1:2])[:, :, None] * freq
+    kernel = torch.exp(-2j * np.pi * kernel)
+    tdata = torch.einsum('ijk,ipk->ijp', kernel, tdata)
+    kernel = (ar - axis_offsets[:, 0:1])[:, :, None] * freq
+    kernel = torch.exp(-2j * np.pi * kernel)
+    return torch.einsum('ijk,ipk->ijp', kernel, tdata)
+
+
+def register_translation_batch(src_image, target_image, upsample_factor=1, space="real"):
+    """ptycho.py:192-248 with cp -> torch.  Returns float64 shifts [S,2] on the device."""
+    if space.lower() == 'fourier':
+        src_freq = src_image
+        target_freq = target_image
+    elif space.lower() == 'real':
+        src_freq = torch.fft.fft2(src_image)
+        target_freq = torch.fft.fft2(target_image)
+    shape = src_freq.shape
+    image_product = src_freq * target_freq.conj()
+    cross_correlation = torch.fft.ifft2(image_product)
+    A = torch.abs(cross_correlation)
+    maxima = A.reshape(A.shape[0], -1).argmax(1)
+    maxima = torch.stack((maxima // shape[2], maxima % shape[2]), dim=1)
+    midpoints = [np.fix(axis_size / 2) for axis_size in shape[1:]]
+    shifts = maxima.to(torch.float64)
+    shifts[:, 0] = torch.where(shifts[:, 0] > midpoints[0], shifts[:, 0] - shape[1], shifts[:, 0])
+    shifts[:, 1] = torch.where(shifts[:, 1] > midpoints[1], shifts[:, 1] - shape[2], shifts[:, 1])
+    if upsample_factor > 1:
+        shifts = torch.round(shifts * upsample_factor) / upsample_factor
+        upsampled_region_size = np.ceil(upsample_factor * 1.5)
+        dftshift = np.fix(upsampled_region_size / 2.0)
+        normalization = (src_freq[0].numel() * upsample_factor ** 2)
+        sample_region_offset = dftshift - shifts * upsample_factor
+        cross_correlation = _upsampled_dft_batch(image_product.conj(), upsampled_region_size,
+                                                 upsample_factor, sample_region_offset).conj()
+        cross_correlation = cross_correlation / normalization
+        A = torch.abs(cross_correlation)
+        maxima = A.reshape(A.shape[0], -1).argmax(1)
+        ups = A.shape[2]
+        maxima = torch.stack((maxima // ups, maxima % ups), dim=1)
+        maxima = maxima.to(torch.float64) - dftshift
+        shifts = shifts + maxima / upsample_factor
+    for dim in range(src_freq.ndim):
+        if shape[dim] == 1:
+            shifts[dim] = 0
+    return shifts
+
+
 class RefCGPtychoSolver(RefPtychoFFT):
     """torch restatement of CGPtychoSolver (ptycho.py:250-488)."""
 
@@ -222,8 +280,13 @@ class RefCGPtychoSolver(RefPtychoFFT):
                 p2 += torch.abs(tmp2) ** 2
                 p3 += 2 * (tmp1.real * tmp2.real + tmp1.imag * tmp2.imag)
             gammapsi = 0.5 * self.line_search_sqr(minf, p1, p2, p3, trials=trials)
-            if self.position_correction and i > 0:
-                raise NotImplementedError("position correction restatement: next round")
+            if self.position_correction and i > 0:  # ptycho.py:398-403
+                tmp1 = self.fwd(psi, scan, probe[:, 0] * 0 + 1)[0]
+                tmp2 = self.fwd(psi + gammapsi * dpsi, scan, probe[:, 0] * 0 + 1)[0]
+                shifts = register_translation_batch(tmp1, tmp2, upsample_factor=100, space='fourier')
+                if getattr(self, "shift_log", None) is not None:
+                    self.shift_log.append(shifts.cpu().numpy())
+                scan[0, :] += shifts
             psi = psi + gammapsi * dpsi
 
             if recover_prb:

@@ -23,6 +23,18 @@ def _pt():
     return pt
 
 
+@pytest.fixture(autouse=True)
+def primary_configuration():
+    """Primary CG parity configuration: the position-correction block (Q5, ptycho.py:398-403) OFF on
+    both sides -- the golden vectors and the oracles' defaults.  The tests named *_position_correction
+    switch it ON on both sides (the solver's default, = the reference's behaviour)."""
+    pt = _pt()
+    saved = pt.CGPtychoSolver.position_correction
+    pt.CGPtychoSolver.position_correction = False
+    yield
+    pt.CGPtychoSolver.position_correction = saved
+
+
 def _problem(nmodes, nscan, model, ndet=128, seed=0, noisy=False):
     """tests/test.py / tests/test_modes.py style problem on the reference fixtures, scaled down."""
     if ndet == 128:
@@ -152,6 +164,49 @@ def test_cg_vs_reference_gpu(nmodes, nscan, model, piter, ndet, noisy):
         print("   free running vs replayed: psi %.2e probe %.2e" % (f_psi, f_prb))
         if mism == 0 and same:
             assert f_psi < TOL and f_prb < TOL
+
+
+@pytest.mark.skipif(not ref_gpu.available(), reason="oracle/_ref not built")
+@pytest.mark.parametrize("nmodes,nscan,model,piter,ndet", [
+    (1, 64, "gaussian", 6, 128),
+    (2, 36, "poisson", 4, 64),
+    (1, 16, "gaussian", 3, 256),
+])
+def test_cg_vs_reference_gpu_position_correction(nmodes, nscan, model, piter, ndet):
+    """`run` as the reference really executes it -- position correction ON (Q5) -- against the
+    reference's cuFFT operators + the cp -> torch restatement of register_translation_batch
+    (cuFFT ifft2 + complex128 einsum) on the same GPU, line-search decisions replayed.  The shifts
+    are argmax picks on a 0.01 px grid: they must agree except where a near-tie falls one grid step
+    apart, and psi / probe must meet the 1e-4 bar."""
+    pt = _pt()
+    data, psi0, scan, prb0 = _problem(nmodes, nscan, model, ndet)
+    nscan = scan.shape[1]
+    nz, n = psi0.shape[1:]
+    with ref_gpu.RefCGPtychoSolver(nscan, ndet, ndet, 1, nz, n) as ref:
+        ref.position_correction = True
+        ref.shift_log = []
+        want = ref.run_batch(data, psi0, scan, prb0, piter=piter, model=model, recover_prb=True,
+                             verbose=False)
+        steps = [t[2] for t in ref.last_trials]
+        rlog = ref.shift_log
+
+    def exact():
+        with O.float64_arithmetic():
+            return O.cg_run(data, psi0, scan.copy(), prb0.copy(), piter, model, True,
+                            forced_steps=list(steps), position_correction=True)
+
+    with pt.CGPtychoSolver(nscan, ndet, ndet, 1, nz, n) as slv:
+        slv.position_correction = True
+        slv._forced_steps = list(steps)
+        got = slv.run_batch(data, psi0, scan, prb0, piter=piter, model=model, recover_prb=True)
+        glog = [x.cpu().numpy() for x in slv.shift_log]
+        assert len(glog) == len(rlog) == piter - 1
+        nbad = sum(int((np.abs(a - b).max(axis=1) > 0).sum()) for a, b in zip(glog, rlog))
+        worst = max(float(np.abs(a - b).max()) for a, b in zip(glog, rlog))
+        print("   shifts: %d of %d positions differ, worst %.3f px, largest shift %.2f px"
+              % (nbad, nscan * len(rlog), worst, max(float(np.abs(b).max()) for b in rlog)))
+        assert worst <= 0.0100001 and nbad <= max(1, nscan * len(rlog) // 50)
+        _assert_parity(got, want, exact, "(position correction) %s" % ((nmodes, nscan, model, piter, ndet),))
 
 
 def test_cg_vs_numpy_oracle_small():
