@@ -536,6 +536,15 @@ int ptx_cg_linesearch(ptx_plan* p, const void* obj_a, const void* prb_a, int nmo
 // ------------------------------------------------------------------------------------------
 // E[j][k] = exp(2 pi i j k_signed / (uf N)), j < U; zero rows up to REG_EROWS.  Rebuilt (stream
 // ordered) only when the upsampling factor changes.
+// PTX_REG_DMMA=0 selects the scalar-DFMA form of the matrix DFT (kept for comparison; profiles/)
+static int reg_use_mma() {
+  static const int on = []() {
+    const char* e = getenv("PTX_REG_DMMA");
+    return (e && e[0] == '0') ? 0 : 1;
+  }();
+  return on;
+}
+
 static int reg_prepare(ptx_plan* p, int uf, int* U_out, cudaStream_t st) {
   if (uf < 1) return fail(PTX_EINVAL, "upsample_factor must be a positive integer");
   const int U = (3 * uf + 1) / 2;  // ceil(1.5 uf)
@@ -581,6 +590,7 @@ int ptx_register_translation(ptx_plan* p, const void* src, const void* target, s
   a.reg_U = U;
   a.reg_uf = upsample_factor;
   a.reg_out = shifts;
+  a.reg_mma = reg_use_mma();
   return launch(p, fourier_space ? K_REG_FOURIER : K_REG_REAL, a, st);
 }
 
@@ -609,6 +619,7 @@ int ptx_cg_position_shifts(ptx_plan* p, const void* psi_a, const void* psi_b, co
   a.reg_U = U;
   a.reg_uf = upsample_factor;
   a.reg_out = shifts;
+  a.reg_mma = reg_use_mma();
   return launch(p, K_REG_OBJ, a, st);
 }
 

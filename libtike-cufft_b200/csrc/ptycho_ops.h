@@ -12,7 +12,7 @@ namespace ptx {
 
 // position correction (ptycho_register.cuh)
 constexpr int REG_UMAX = 150;   // largest upsampled window: ceil(1.5 * 100)
-constexpr int REG_EROWS = 192;  // rows of the E table (zero beyond U: padded chunks contribute |G| = 0)
+constexpr int REG_EROWS = 256;  // rows of the E table (zero beyond U: padded chunks contribute |G| = 0)
 
 // kernel parameter block, shared by every pass
 struct PassArgs {
@@ -42,6 +42,7 @@ struct PassArgs {
   const double2* reg_E;  // [REG_EROWS][N] table W^(j k), W = exp(2 pi i / (uf N))
   double* reg_out;       // [npat][2] shifts (row, col)
   int reg_U, reg_uf;     // upsampled window size ceil(1.5 uf), upsampling factor
+  int reg_mma;           // matrix DFT on the FP64 tensor cores (DMMA) instead of scalar DFMA
 };
 
 enum KernelId {

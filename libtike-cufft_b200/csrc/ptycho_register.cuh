@@ -50,6 +50,31 @@ struct RegCfg<Plan<9>> {
   static constexpr int JC = 8, KCH = 4, TJR = 3, TJC = 1;
 };
 
+// Geometry of the tensor-core (DMMA, mma.sync.m8n8k4.f64) form of the same two products.  A warp owns
+// 8 window columns x 32 rows (stage 1: 4 C tiles) and 8 columns x MT2 row tiles (stage 2); a complex
+// tile product is 4 real DMMAs on fragments that ONE 128-bit shared load per lane delivers (re, im).
+// Operand traffic is ~0.3 B per FMA instead of the 3 B of the scalar-DFMA register tiles, which ncu
+// showed to be bound by the shared-memory data pipe (profiles/r01i_register128_ncu.txt).
+template <class P>
+struct RegMma {
+  using C = RegCfg<P>;
+  static constexpr int N = P::N, NT = P::NT, NW = NT / 32;
+  static constexpr int JC = C::JC, KCH = C::KCH;
+  static constexpr int KP = (KCH % 8 == 4) ? KCH : KCH + 4;  // pitch = 4 mod 8 complex128: the two
+  static constexpr int TP = N + 4;                           // rows of a quarter warp hit disjoint banks
+  static constexpr int W1J = JC / 8, W1R = NW / W1J, RCH = 32 * W1R;
+  static constexpr int W2C = JC / 8, W2R = NW / W2C;
+  static constexpr int NTILE = (REG_UMAX + 7) / 8;                       // 19 row tiles of 8 cover U <= 150
+  static constexpr int MT2 = W2R >= NTILE ? 1 : (W2R == 1 ? 5 : (NTILE + W2R - 1) / W2R);
+  static constexpr int JRCH = 8 * MT2 * W2R;                             // window rows per stage-2 pass
+  static constexpr int SZ_A = JC * KP, SZ_B = RCH * KP, SZ_A2 = JRCH * KP;
+  static constexpr int SZ_AB = (SZ_A + SZ_B) > SZ_A2 ? (SZ_A + SZ_B) : SZ_A2;
+  static constexpr int OFF_T = SZ_AB, OFF_PH = OFF_T + JC * TP, TOTAL = OFF_PH + 2 * N;
+  static constexpr size_t BYTES = (size_t)TOTAL * 16;
+  static_assert(W1J * W1R == NW && W2C * W2R == NW && N % RCH == 0 && N % KCH == 0 && KCH % 4 == 0, "tiling");
+  static_assert(REG_EROWS % JC == 0 && REG_EROWS >= ((REG_UMAX + JRCH - 1) / JRCH) * JRCH, "E rows");
+};
+
 template <class P>
 struct RegGeom {
   using C = RegCfg<P>;
@@ -65,7 +90,8 @@ struct RegGeom {
   static constexpr int SZ_A = JC * KP, SZ_B = RCH * KP, SZ_A2 = JRCH * KP;
   static constexpr int SZ_AB = (SZ_A + SZ_B) > SZ_A2 ? (SZ_A + SZ_B) : SZ_A2;
   static constexpr int OFF_T = SZ_AB, OFF_PH = OFF_T + JC * TP, TOTAL = OFF_PH + 2 * N;
-  static constexpr size_t BYTES = (size_t)TOTAL * 16;
+  static constexpr size_t BYTES_FMA = (size_t)TOTAL * 16;
+  static constexpr size_t BYTES = BYTES_FMA > RegMma<P>::BYTES ? BYTES_FMA : RegMma<P>::BYTES;
   // the GEMM region reuses the FFT tile when it fits, else it follows the mbarriers
   static constexpr bool IN_TILE = BYTES <= Smem<P>::OFF_TW;
   static constexpr size_t OFF = IN_TILE ? 0 : Smem<P>::OFF_DBUF;
@@ -173,20 +199,45 @@ __device__ __forceinline__ int register_refine(const float2* __restrict__ praw,
       for (int i = 0; i < 2; ++i)
 #pragma unroll
         for (int q = 0; q < 4; ++q) acc[i][q] = make_double2(0.0, 0.0);
+      // the global loads of chunk k0 + KCH are issued before chunk k0 is consumed: their L2 latency
+      // hides behind the DFMA work of a whole chunk
+      constexpr int NA = (JC * KCH + NT - 1) / NT, NB = (G::RCH * KCH + NT - 1) / NT;
+      double2 ra[NA];
+      float2 rb[NB];
+      auto fetch1 = [&](int k0) {
+#pragma unroll
+        for (int u = 0; u < NA; ++u) {
+          const int t = tid + u * NT;
+          if (JC * KCH % NT == 0 || t < JC * KCH)
+            ra[u] = __ldg(E + (size_t)(jc0 + t / KCH) * N + k0 + t % KCH);
+        }
+#pragma unroll
+        for (int u = 0; u < NB; ++u) {
+          const int t = tid + u * NT;
+          if (G::RCH * KCH % NT == 0 || t < G::RCH * KCH)
+            rb[u] = __ldcg(praw + (size_t)(r0 + t / KCH) * N + k0 + t % KCH);
+        }
+      };
+      fetch1(0);
       for (int k0 = 0; k0 < N; k0 += KCH) {
         __syncthreads();  // the previous tiles (and, first time round, the phase vectors) are settled
-        for (int t = tid; t < JC * KCH; t += NT) {
-          const int j = t / KCH, kk = t % KCH;
-          As[j * KP + kk] = __ldg(E + (size_t)(jc0 + j) * N + k0 + kk);
+#pragma unroll
+        for (int u = 0; u < NA; ++u) {
+          const int t = tid + u * NT;
+          if (JC * KCH % NT == 0 || t < JC * KCH) As[(t / KCH) * KP + t % KCH] = ra[u];
         }
-        for (int t = tid; t < G::RCH * KCH; t += NT) {
-          const int r = t / KCH, kk = t % KCH;
-          const float2 pv = __ldcg(praw + (size_t)(r0 + r) * N + k0 + kk);
-          const double2 ph = phc[k0 + kk];
-          Bs[r * KP + kk] = make_double2((double)pv.x * ph.x - (double)pv.y * ph.y,
-                                         (double)pv.x * ph.y + (double)pv.y * ph.x);
+#pragma unroll
+        for (int u = 0; u < NB; ++u) {
+          const int t = tid + u * NT;
+          if (G::RCH * KCH % NT == 0 || t < G::RCH * KCH) {
+            const double2 ph = phc[k0 + t % KCH];
+            const float2 pv = rb[u];
+            Bs[(t / KCH) * KP + t % KCH] = make_double2((double)pv.x * ph.x - (double)pv.y * ph.y,
+                                                        (double)pv.x * ph.y + (double)pv.y * ph.x);
+          }
         }
         __syncthreads();
+        if (k0 + KCH < N) fetch1(k0 + KCH);
         const double2* ap = As + (tjl + 8 * w1j) * KP;
         const double2* bp = Bs + (trl + 32 * w1r) * KP;
 #pragma unroll 4
@@ -218,13 +269,26 @@ __device__ __forceinline__ int register_refine(const float2* __restrict__ praw,
       for (int i = 0; i < G::TJR; ++i)
 #pragma unroll
         for (int q = 0; q < G::TJC; ++q) acc[i][q] = make_double2(0.0, 0.0);
+      constexpr int NA2 = (G::JRCH * KCH + NT - 1) / NT;
+      double2 ra2[NA2];
+      auto fetch2 = [&](int k0) {
+#pragma unroll
+        for (int u = 0; u < NA2; ++u) {
+          const int t = tid + u * NT;
+          if (G::JRCH * KCH % NT == 0 || t < G::JRCH * KCH)
+            ra2[u] = __ldg(E + (size_t)(jr0 + t / KCH) * N + k0 + t % KCH);
+        }
+      };
+      fetch2(0);
       for (int k0 = 0; k0 < N; k0 += KCH) {
         __syncthreads();  // stage-1 tiles / previous A2 tile consumed, T complete
-        for (int t = tid; t < G::JRCH * KCH; t += NT) {
-          const int j = t / KCH, kk = t % KCH;
-          A2s[j * KP + kk] = __ldg(E + (size_t)(jr0 + j) * N + k0 + kk);
+#pragma unroll
+        for (int u = 0; u < NA2; ++u) {
+          const int t = tid + u * NT;
+          if (G::JRCH * KCH % NT == 0 || t < G::JRCH * KCH) A2s[(t / KCH) * KP + t % KCH] = ra2[u];
         }
         __syncthreads();
+        if (k0 + KCH < N) fetch2(k0 + KCH);
         const double2* ap = A2s + (rl + 4 * G::TJR * w2r) * KP;
         const double2* bp = Ts + (cl + 8 * G::TJC * w2c) * G::TP + k0;
 #pragma unroll 4
@@ -250,6 +314,171 @@ __device__ __forceinline__ int register_refine(const float2* __restrict__ praw,
             const double2 a = acc[i][q];
             bestd_take(best, a.x * a.x + a.y * a.y, jr * U + jc);
           }
+        }
+    }
+  }
+  return block_argmax<G::NW>(best, red, tid);
+}
+
+__device__ __forceinline__ void dmma(double (&c)[2], double a, double b) {
+  asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};"
+               : "+d"(c[0]), "+d"(c[1])
+               : "d"(a), "d"(b));
+}
+
+// Tensor-core form of register_refine: same chunking, staging and results (up to summation order).
+template <class P>
+__device__ __forceinline__ int register_refine_mma(const float2* __restrict__ praw,
+                                                   const double2* __restrict__ E, double2* sm,
+                                                   double* red, int tid, int sy, int sx, int U, int uf,
+                                                   int dftshift) {
+  using G = RegMma<P>;
+  constexpr int N = G::N, NT = G::NT, KP = G::KP, KCH = G::KCH, JC = G::JC, TP = G::TP;
+  double2* As = sm;
+  double2* Bs = sm + G::SZ_A;
+  double2* A2s = sm;
+  double2* Ts = sm + G::OFF_T;
+  double2* phr = sm + G::OFF_PH;
+  double2* phc = phr + N;
+  const int lane = tid & 31, warp = tid >> 5;
+  const int period = uf * N;
+  for (int k = tid; k < 2 * N; k += NT) {
+    const int kk = k < N ? k : k - N;
+    const int ks = kk < N / 2 ? kk : kk - N;
+    const int m = (k < N ? sy : sx) * uf - dftshift;
+    long long q = ((long long)m * ks) % period;
+    if (q < 0) q += period;
+    double s, c;
+    sincospi(2.0 * (double)q / (double)period, &s, &c);
+    (k < N ? phr : phc)[kk] = make_double2(c, s);
+  }
+  const int fr = lane >> 2, fk = lane & 3;  // fragment row (A: m, B: n) and k index of this lane
+  const int w1j = warp % G::W1J, w1r = warp / G::W1J;
+  const int w2c = warp % G::W2C, w2r = warp / G::W2C;
+  BestD best;
+  best.v = -1.0;
+  best.i = 0;
+  for (int jc0 = 0; jc0 < U; jc0 += JC) {
+    // ---------------- stage 1: T[jc][r] = ph_r[r] sum_c E[jc0+jc][c] P[r][c] ph_c[c]
+    for (int r0 = 0; r0 < N; r0 += G::RCH) {
+      double cre[4][2], cim[4][2];
+#pragma unroll
+      for (int q = 0; q < 4; ++q) cre[q][0] = cre[q][1] = cim[q][0] = cim[q][1] = 0.0;
+      constexpr int NA = (JC * KCH + NT - 1) / NT, NB = (G::RCH * KCH + NT - 1) / NT;
+      double2 ra[NA];
+      float2 rb[NB];
+      auto fetch1 = [&](int k0) {
+#pragma unroll
+        for (int u = 0; u < NA; ++u) {
+          const int t = tid + u * NT;
+          if (JC * KCH % NT == 0 || t < JC * KCH)
+            ra[u] = __ldg(E + (size_t)(jc0 + t / KCH) * N + k0 + t % KCH);
+        }
+#pragma unroll
+        for (int u = 0; u < NB; ++u) {
+          const int t = tid + u * NT;
+          if (G::RCH * KCH % NT == 0 || t < G::RCH * KCH)
+            rb[u] = __ldcg(praw + (size_t)(r0 + t / KCH) * N + k0 + t % KCH);
+        }
+      };
+      fetch1(0);
+      for (int k0 = 0; k0 < N; k0 += KCH) {
+        __syncthreads();
+#pragma unroll
+        for (int u = 0; u < NA; ++u) {
+          const int t = tid + u * NT;
+          if (JC * KCH % NT == 0 || t < JC * KCH) As[(t / KCH) * KP + t % KCH] = ra[u];
+        }
+#pragma unroll
+        for (int u = 0; u < NB; ++u) {
+          const int t = tid + u * NT;
+          if (G::RCH * KCH % NT == 0 || t < G::RCH * KCH) {
+            const double2 ph = phc[k0 + t % KCH];
+            const float2 pv = rb[u];
+            Bs[(t / KCH) * KP + t % KCH] = make_double2((double)pv.x * ph.x - (double)pv.y * ph.y,
+                                                        (double)pv.x * ph.y + (double)pv.y * ph.x);
+          }
+        }
+        __syncthreads();
+        if (k0 + KCH < N) fetch1(k0 + KCH);
+        const double2* ap = As + (8 * w1j + fr) * KP + fk;
+        const double2* bp = Bs + (32 * w1r + fr) * KP + fk;
+#pragma unroll
+        for (int kk = 0; kk < KCH; kk += 4) {
+          const double2 a = ap[kk];
+          const double nai = -a.y;
+#pragma unroll
+          for (int q = 0; q < 4; ++q) {
+            const double2 b = bp[8 * q * KP + kk];
+            dmma(cre[q], a.x, b.x);
+            dmma(cre[q], nai, b.y);
+            dmma(cim[q], a.x, b.y);
+            dmma(cim[q], a.y, b.x);
+          }
+        }
+      }
+      // C fragment: row = fr (window column), columns 2 fk + {0, 1} (rows r of the n tile)
+#pragma unroll
+      for (int q = 0; q < 4; ++q)
+#pragma unroll
+        for (int u = 0; u < 2; ++u) {
+          const int r = r0 + 32 * w1r + 8 * q + 2 * fk + u;
+          const double2 ph = phr[r];
+          const double ax = cre[q][u], ay = cim[q][u];
+          Ts[(8 * w1j + fr) * TP + r] = make_double2(ax * ph.x - ay * ph.y, ax * ph.y + ay * ph.x);
+        }
+    }
+    // ---------------- stage 2: G[jr][jc0+jc] = sum_r E[jr][r] T[jc][r]
+    for (int jr0 = 0; jr0 < U; jr0 += G::JRCH) {
+      double cre[G::MT2][2], cim[G::MT2][2];
+#pragma unroll
+      for (int i = 0; i < G::MT2; ++i) cre[i][0] = cre[i][1] = cim[i][0] = cim[i][1] = 0.0;
+      constexpr int NA2 = (G::JRCH * KCH + NT - 1) / NT;
+      double2 ra2[NA2];
+      auto fetch2 = [&](int k0) {
+#pragma unroll
+        for (int u = 0; u < NA2; ++u) {
+          const int t = tid + u * NT;
+          if (G::JRCH * KCH % NT == 0 || t < G::JRCH * KCH)
+            ra2[u] = __ldg(E + (size_t)(jr0 + t / KCH) * N + k0 + t % KCH);
+        }
+      };
+      fetch2(0);
+      for (int k0 = 0; k0 < N; k0 += KCH) {
+        __syncthreads();
+#pragma unroll
+        for (int u = 0; u < NA2; ++u) {
+          const int t = tid + u * NT;
+          if (G::JRCH * KCH % NT == 0 || t < G::JRCH * KCH) A2s[(t / KCH) * KP + t % KCH] = ra2[u];
+        }
+        __syncthreads();
+        if (k0 + KCH < N) fetch2(k0 + KCH);
+        const double2* ap = A2s + (8 * G::MT2 * w2r + fr) * KP + fk;
+        const double2* bp = Ts + (8 * w2c + fr) * TP + k0 + fk;
+#pragma unroll
+        for (int kk = 0; kk < KCH; kk += 4) {
+          const double2 b = bp[kk];
+          const double nbi = -b.y;
+#pragma unroll
+          for (int i = 0; i < G::MT2; ++i) {
+            if (jr0 + 8 * (G::MT2 * w2r + i) < U) {  // warp-uniform: tiles beyond the window are skipped
+              const double2 a = ap[8 * i * KP + kk];
+              dmma(cre[i], a.x, b.x);
+              dmma(cre[i], a.y, nbi);
+              dmma(cim[i], a.x, b.y);
+              dmma(cim[i], a.y, b.x);
+            }
+          }
+        }
+      }
+#pragma unroll
+      for (int i = 0; i < G::MT2; ++i)
+#pragma unroll
+        for (int u = 0; u < 2; ++u) {
+          const int jr = jr0 + 8 * (G::MT2 * w2r + i) + fr;
+          const int jc = jc0 + 8 * w2c + 2 * fk + u;
+          if (jr < U && jc < U)
+            bestd_take(best, cre[i][u] * cre[i][u] + cim[i][u] * cim[i][u], jr * U + jc);
         }
     }
   }
@@ -355,7 +584,9 @@ __global__ void __launch_bounds__(P::NT) k_register(const PassArgs a,
     if (sx > P::N / 2) sx -= P::N;
     double oy = (double)sy, ox = (double)sx;
     if (uf > 1) {
-      const int j = register_refine<P>(praw, a.reg_E, gemm, c.red, c.tid, sy, sx, U, uf, dftshift);
+      const int j = a.reg_mma
+                        ? register_refine_mma<P>(praw, a.reg_E, gemm, c.red, c.tid, sy, sx, U, uf, dftshift)
+                        : register_refine<P>(praw, a.reg_E, gemm, c.red, c.tid, sy, sx, U, uf, dftshift);
       oy += (double)(j / U - dftshift) / (double)uf;
       ox += (double)(j % U - dftshift) / (double)uf;
     }
