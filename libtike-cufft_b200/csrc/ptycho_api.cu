@@ -159,6 +159,7 @@ struct ptx_plan {
   Geo geo;
   // position correction (lazy): E table of the last upsampling factor, all-ones probe
   double2* reg_E;
+  double* reg_AT;  // [REG_NQ][N] Bessel table followed by [REG_JROWS][REG_NQ] Chebyshev table
   int reg_uf;
   float2* ones;
 };
@@ -333,6 +334,7 @@ int ptx_create(ptx_plan** out, size_t ptheta, size_t nz, size_t n, size_t nscan,
   p->tw = nullptr;
   p->scratch = nullptr;
   p->reg_E = nullptr;
+  p->reg_AT = nullptr;
   p->reg_uf = 0;
   p->ones = nullptr;
   p->geo.T = (int)ptheta; p->geo.nz = (int)nz; p->geo.n = (int)n; p->geo.S = (int)nscan;
@@ -367,10 +369,12 @@ int ptx_free(ptx_plan* p) {
     cudaFree(p->tw);
     cudaFree(p->scratch);
     if (p->reg_E) cudaFree(p->reg_E);
+    if (p->reg_AT) cudaFree(p->reg_AT);
     if (p->ones) cudaFree(p->ones);
     p->tw = nullptr;
     p->scratch = nullptr;
     p->reg_E = nullptr;
+    p->reg_AT = nullptr;
     p->ones = nullptr;
     p->freed = true;
   }
@@ -536,13 +540,40 @@ int ptx_cg_linesearch(ptx_plan* p, const void* obj_a, const void* prb_a, int nmo
 // ------------------------------------------------------------------------------------------
 // E[j][k] = exp(2 pi i j k_signed / (uf N)), j < U; zero rows up to REG_EROWS.  Rebuilt (stream
 // ordered) only when the upsampling factor changes.
-// PTX_REG_DMMA=0 selects the scalar-DFMA form of the matrix DFT (kept for comparison; profiles/)
-static int reg_use_mma() {
-  static const int on = []() {
-    const char* e = getenv("PTX_REG_DMMA");
-    return (e && e[0] == '0') ? 0 : 1;
+// PTX_REG_ALGO = lowrank (default: Jacobi-Anger factorisation of the window kernel on the FP64
+// tensor cores) | dmma (the reference's two matrix products, on the tensor cores) | dfma (same, on
+// the scalar FP64 pipe).  All three give the same shifts (tests/test_gpu_register.py).
+static int reg_algo() {
+  static const int algo = []() {
+    const char* e = getenv("PTX_REG_ALGO");
+    return !e ? 2 : !strcmp(e, "dfma") ? 0 : !strcmp(e, "dmma") ? 1 : 2;
   }();
-  return on;
+  return algo;
+}
+
+// J_0..J_{nmax-1}(x) by Miller's backward recurrence, normalised with J_0 + 2 sum J_2k = 1
+static void bessel_j(long double x, int nmax, long double* out) {
+  const long double ax = fabsl(x);
+  if (ax < 1e-30L) {
+    for (int n = 0; n < nmax; ++n) out[n] = n == 0 ? 1.0L : 0.0L;
+    return;
+  }
+  const int start = nmax + 40;  // x <= 0.75 pi: J_n decays like (x/2)^n / n!, far below 1e-40 here
+  long double jp1 = 0.0L, j = 1e-300L, sum = 0.0L;
+  std::vector<long double> v(start + 1, 0.0L);
+  for (int n = start; n >= 1; --n) {  // J_{n-1} = (2n/x) J_n - J_{n+1}
+    const long double jm1 = (2.0L * n / ax) * j - jp1;
+    jp1 = j;
+    j = jm1;
+    v[n - 1] = j;
+    if (((n - 1) & 1) == 0 && n - 1 > 0) sum += 2.0L * j;
+  }
+  sum += v[0];
+  for (int n = 0; n < nmax; ++n) {
+    long double r = v[n] / sum;
+    if (x < 0 && (n & 1)) r = -r;  // J_n(-x) = (-1)^n J_n(x)
+    out[n] = r;
+  }
 }
 
 static int reg_prepare(ptx_plan* p, int uf, int* U_out, cudaStream_t st) {
@@ -565,8 +596,31 @@ static int reg_prepare(ptx_plan* p, int uf, int* U_out, cudaStream_t st) {
       const long double ang = PI2 * (long double)q / (long double)period;
       h[(size_t)j * N + k] = make_double2((double)cosl(ang), (double)sinl(ang));
     }
-  CUDA_TRY(cudaStreamSynchronize(st));  // a previous launch may still read the old table
+  // low-rank form: a[n][k] = eps_n J_n(theta_k), theta_k = 2 pi dftshift k_signed / (uf N);
+  // T[j][n] = T_n(x_j), x_j = (j - dftshift) / dftshift, zero rows beyond U
+  const int dftshift = U / 2;
+  const size_t na = (size_t)REG_NQ * N, nt = (size_t)REG_JROWS * REG_NQ;
+  if (!p->reg_AT) CUDA_TRY(cudaMalloc(&p->reg_AT, (na + nt) * sizeof(double)));
+  std::vector<double> hat(na + nt, 0.0);
+  for (size_t k = 0; k < N; ++k) {
+    const long long ks = k < N / 2 ? (long long)k : (long long)k - (long long)N;
+    long double jn[REG_NQ];
+    bessel_j(PI2 * (long double)dftshift * (long double)ks / (long double)period, REG_NQ, jn);
+    for (int n = 0; n < REG_NQ; ++n) hat[(size_t)n * N + k] = (double)((n ? 2.0L : 1.0L) * jn[n]);
+  }
+  for (int j = 0; j < U; ++j) {
+    const long double x = dftshift ? (long double)(j - dftshift) / (long double)dftshift : 0.0L;
+    long double t0 = 1.0L, t1 = x;
+    for (int n = 0; n < REG_NQ; ++n) {  // T_{n+1} = 2 x T_n - T_{n-1}
+      hat[na + (size_t)j * REG_NQ + n] = (double)t0;
+      const long double t2 = 2.0L * x * t1 - t0;
+      t0 = t1;
+      t1 = t2;
+    }
+  }
+  CUDA_TRY(cudaStreamSynchronize(st));  // a previous launch may still read the old tables
   CUDA_TRY(cudaMemcpy(p->reg_E, h.data(), count * sizeof(double2), cudaMemcpyHostToDevice));
+  CUDA_TRY(cudaMemcpy(p->reg_AT, hat.data(), hat.size() * sizeof(double), cudaMemcpyHostToDevice));
   p->reg_uf = uf;
   return PTX_OK;
 }
@@ -590,7 +644,9 @@ int ptx_register_translation(ptx_plan* p, const void* src, const void* target, s
   a.reg_U = U;
   a.reg_uf = upsample_factor;
   a.reg_out = shifts;
-  a.reg_mma = reg_use_mma();
+  a.reg_A = p->reg_AT;
+  a.reg_T = p->reg_AT ? p->reg_AT + (size_t)REG_NQ * p->ndet : nullptr;
+  a.reg_algo = reg_algo();
   return launch(p, fourier_space ? K_REG_FOURIER : K_REG_REAL, a, st);
 }
 
@@ -619,7 +675,9 @@ int ptx_cg_position_shifts(ptx_plan* p, const void* psi_a, const void* psi_b, co
   a.reg_U = U;
   a.reg_uf = upsample_factor;
   a.reg_out = shifts;
-  a.reg_mma = reg_use_mma();
+  a.reg_A = p->reg_AT;
+  a.reg_T = p->reg_AT ? p->reg_AT + (size_t)REG_NQ * p->ndet : nullptr;
+  a.reg_algo = reg_algo();
   return launch(p, K_REG_OBJ, a, st);
 }
 

@@ -12,7 +12,9 @@ namespace ptx {
 
 // position correction (ptycho_register.cuh)
 constexpr int REG_UMAX = 150;   // largest upsampled window: ceil(1.5 * 100)
-constexpr int REG_EROWS = 256;  // rows of the E table (zero beyond U: padded chunks contribute |G| = 0)
+constexpr int REG_EROWS = 256;
+constexpr int REG_NQ = 24;      // terms of the Jacobi-Anger expansion of the window kernel (ptycho_register.cuh)
+constexpr int REG_JROWS = 160;  // rows of the Chebyshev table T[j][n] (zero beyond U)  // rows of the E table (zero beyond U: padded chunks contribute |G| = 0)
 
 // kernel parameter block, shared by every pass
 struct PassArgs {
@@ -42,7 +44,9 @@ struct PassArgs {
   const double2* reg_E;  // [REG_EROWS][N] table W^(j k), W = exp(2 pi i / (uf N))
   double* reg_out;       // [npat][2] shifts (row, col)
   int reg_U, reg_uf;     // upsampled window size ceil(1.5 uf), upsampling factor
-  int reg_mma;           // matrix DFT on the FP64 tensor cores (DMMA) instead of scalar DFMA
+  const double* reg_A;   // [REG_NQ][N] eps_n J_n(theta_k)
+  const double* reg_T;   // [REG_JROWS][REG_NQ] T_n(x_j)
+  int reg_algo;          // 2: low-rank (Jacobi-Anger) on DMMA; 1: direct products on DMMA; 0: on DFMA
 };
 
 enum KernelId {

@@ -75,6 +75,38 @@ struct RegMma {
   static_assert(REG_EROWS % JC == 0 && REG_EROWS >= ((REG_UMAX + JRCH - 1) / JRCH) * JRCH, "E rows");
 };
 
+// Geometry of the low-rank (Jacobi-Anger) form.  The matrix-DFT kernel over the 1.5-pixel window,
+//   W^((j - dftshift) k) = exp(i theta_k x_j),  theta_k = 2 pi dftshift k / (uf N) in [-0.75 pi, 0.75 pi],
+//   x_j = (j - dftshift) / dftshift in [-1, 1],
+// has numerical rank ~20:  exp(i theta x) = sum_n eps_n i^n J_n(theta) T_n(x)  (eps_0 = 1, eps_n = 2),
+// and J_n(0.75 pi) < 1e-20 for n >= 24.  With a[n][k] = eps_n J_n(theta_k) (real) and T[j][n] = T_n(x_j)
+//   G = T (i^(n+m) D) T^t,   D[n][m] = sum_r a[n][r] ph_r[r] (sum_c a[m][c] ph_c[c] P[r][c]),
+// i.e. 24 N^2 + 24^2 N + 24^2 U + 24 U^2 real-times-complex multiply-adds instead of U N^2 + U^2 N
+// complex ones: 12x fewer FP64 operations at N = 128, 20x at N = 256, equal to the direct products
+// to rounding (2.7e-15 of the peak, tests/test_register_oracle.py).  All four products run on the
+// FP64 tensor cores (2 DMMAs per real-times-complex tile step).
+template <class P>
+struct RegCheb {
+  static constexpr int N = P::N, NT = P::NT, NW = NT / 32;
+  static constexpr int NQ = REG_NQ, QT = NQ / 8;     // expansion terms, in tiles of 8
+  static constexpr int KCH = N >= 512 ? 8 : 16;      // contraction chunk of stage 1
+  static constexpr int KP = KCH + 4;                 // pitch of the staged A (real) / B (complex) tiles
+  static constexpr int RCH = N < 128 ? N : 128;      // image rows per pass of stages 1-2
+  static constexpr int NTW = (RCH / 8) / NW;         // stage-1 row tiles per warp
+  static constexpr int DP = RCH + 4;                 // pitch of a2s / D1s
+  static constexpr int QP = NQ + 4;                  // pitch of Tsm / Ds / Hs
+  static constexpr int PPW = (QT * QT + NW - 1) / NW;  // stage-2 tile pairs per warp
+  static constexpr int JROWS = 160;                  // window rows/cols rounded up to tiles (U <= 150)
+  // phase A (bytes): ph | As | Bs | a2s | D1s        phase B: Tsm | Ds | Hs   (same region)
+  static constexpr size_t A_PH = 0, A_AS = A_PH + (size_t)2 * N * 16, A_BS = A_AS + (size_t)NQ * KP * 8,
+                          A_A2 = A_BS + (size_t)RCH * KP * 16, A_D1 = A_A2 + (size_t)NQ * DP * 8,
+                          A_END = A_D1 + (size_t)NQ * DP * 16;
+  static constexpr size_t B_T = 0, B_DS = B_T + (size_t)JROWS * QP * 8, B_HS = B_DS + (size_t)NQ * QP * 16,
+                          B_END = B_HS + (size_t)JROWS * QP * 16;
+  static constexpr size_t BYTES = A_END > B_END ? A_END : B_END;
+  static_assert(NTW >= 1 && NTW * NW * 8 == RCH && N % RCH == 0 && N % KCH == 0, "tiling");
+};
+
 template <class P>
 struct RegGeom {
   using C = RegCfg<P>;
@@ -91,7 +123,8 @@ struct RegGeom {
   static constexpr int SZ_AB = (SZ_A + SZ_B) > SZ_A2 ? (SZ_A + SZ_B) : SZ_A2;
   static constexpr int OFF_T = SZ_AB, OFF_PH = OFF_T + JC * TP, TOTAL = OFF_PH + 2 * N;
   static constexpr size_t BYTES_FMA = (size_t)TOTAL * 16;
-  static constexpr size_t BYTES = BYTES_FMA > RegMma<P>::BYTES ? BYTES_FMA : RegMma<P>::BYTES;
+  static constexpr size_t BYTES_DIRECT = BYTES_FMA > RegMma<P>::BYTES ? BYTES_FMA : RegMma<P>::BYTES;
+  static constexpr size_t BYTES = BYTES_DIRECT > RegCheb<P>::BYTES ? BYTES_DIRECT : RegCheb<P>::BYTES;
   // the GEMM region reuses the FFT tile when it fits, else it follows the mbarriers
   static constexpr bool IN_TILE = BYTES <= Smem<P>::OFF_TW;
   static constexpr size_t OFF = IN_TILE ? 0 : Smem<P>::OFF_DBUF;
@@ -485,6 +518,213 @@ __device__ __forceinline__ int register_refine_mma(const float2* __restrict__ pr
   return block_argmax<G::NW>(best, red, tid);
 }
 
+__device__ __forceinline__ double2 rot_i(double x, double y, int q) {  // (x + i y) * i^q
+  switch (q & 3) {
+    case 0: return make_double2(x, y);
+    case 1: return make_double2(-y, x);
+    case 2: return make_double2(-x, -y);
+    default: return make_double2(y, -x);
+  }
+}
+
+// Low-rank form of the refinement (see RegCheb).  atab: [NQ][N] doubles, ttab: [JROWS][NQ] doubles.
+template <class P>
+__device__ __forceinline__ int register_refine_cheb(const float2* __restrict__ praw,
+                                                    const double* __restrict__ atab,
+                                                    const double* __restrict__ ttab,
+                                                    unsigned char* smraw, double* red, int tid, int sy,
+                                                    int sx, int U) {
+  using G = RegCheb<P>;
+  constexpr int N = G::N, NT = G::NT, NW = G::NW, NQ = G::NQ, QT = G::QT, KCH = G::KCH, KP = G::KP;
+  constexpr int RCH = G::RCH, NTW = G::NTW, DP = G::DP, QP = G::QP, PPW = G::PPW;
+  double2* phr = reinterpret_cast<double2*>(smraw + G::A_PH);
+  double2* phc = phr + N;
+  double* As = reinterpret_cast<double*>(smraw + G::A_AS);
+  double2* Bs = reinterpret_cast<double2*>(smraw + G::A_BS);
+  double* a2s = reinterpret_cast<double*>(smraw + G::A_A2);
+  double2* D1s = reinterpret_cast<double2*>(smraw + G::A_D1);
+  double* Tsm = reinterpret_cast<double*>(smraw + G::B_T);
+  double2* Ds = reinterpret_cast<double2*>(smraw + G::B_DS);
+  double2* Hs = reinterpret_cast<double2*>(smraw + G::B_HS);
+  const int lane = tid & 31, warp = tid >> 5, fr = lane >> 2, fk = lane & 3;
+  // whole-pixel shift as a phase ramp: ph[k] = exp(2 pi i s k_signed / N)
+  for (int k = tid; k < 2 * N; k += NT) {
+    const int kk = k < N ? k : k - N;
+    const int ks = kk < N / 2 ? kk : kk - N;
+    int q = ((k < N ? sy : sx) * ks) % N;
+    if (q < 0) q += N;
+    double sn, cs;
+    sincospi(2.0 * (double)q / (double)N, &sn, &cs);
+    (k < N ? phr : phc)[kk] = make_double2(cs, sn);
+  }
+  double d2re[PPW][2], d2im[PPW][2];
+#pragma unroll
+  for (int s = 0; s < PPW; ++s) d2re[s][0] = d2re[s][1] = d2im[s][0] = d2im[s][1] = 0.0;
+  for (int r0 = 0; r0 < N; r0 += RCH) {
+    __syncthreads();  // stage 2 of the previous pass is done with a2s / D1s; ph is settled
+    for (int t = tid; t < NQ * RCH; t += NT) a2s[(t / RCH) * DP + t % RCH] = __ldg(atab + (size_t)(t / RCH) * N + r0 + t % RCH);
+    // ---------------- stage 1: D1[m][r] = ph_r[r] sum_c a[m][c] ph_c[c] P[r][c]
+    double cre[QT][NTW][2], cim[QT][NTW][2];
+#pragma unroll
+    for (int i = 0; i < QT; ++i)
+#pragma unroll
+      for (int q = 0; q < NTW; ++q) cre[i][q][0] = cre[i][q][1] = cim[i][q][0] = cim[i][q][1] = 0.0;
+    constexpr int NA = (NQ * KCH + NT - 1) / NT, NB = (RCH * KCH + NT - 1) / NT;
+    double ra[NA];
+    float2 rb[NB];
+    auto fetch1 = [&](int k0) {
+#pragma unroll
+      for (int u = 0; u < NA; ++u) {
+        const int t = tid + u * NT;
+        if (t < NQ * KCH) ra[u] = __ldg(atab + (size_t)(t / KCH) * N + k0 + t % KCH);
+      }
+#pragma unroll
+      for (int u = 0; u < NB; ++u) {
+        const int t = tid + u * NT;
+        if (RCH * KCH % NT == 0 || t < RCH * KCH)
+          rb[u] = __ldcg(praw + (size_t)(r0 + t / KCH) * N + k0 + t % KCH);
+      }
+    };
+    fetch1(0);
+    for (int k0 = 0; k0 < N; k0 += KCH) {
+      __syncthreads();
+#pragma unroll
+      for (int u = 0; u < NA; ++u) {
+        const int t = tid + u * NT;
+        if (t < NQ * KCH) As[(t / KCH) * KP + t % KCH] = ra[u];
+      }
+#pragma unroll
+      for (int u = 0; u < NB; ++u) {
+        const int t = tid + u * NT;
+        if (RCH * KCH % NT == 0 || t < RCH * KCH) {
+          const double2 ph = phc[k0 + t % KCH];
+          const float2 pv = rb[u];
+          Bs[(t / KCH) * KP + t % KCH] = make_double2((double)pv.x * ph.x - (double)pv.y * ph.y,
+                                                      (double)pv.x * ph.y + (double)pv.y * ph.x);
+        }
+      }
+      __syncthreads();
+      if (k0 + KCH < N) fetch1(k0 + KCH);
+      const double* ap = As + fr * KP + fk;
+      const double2* bp = Bs + (8 * NTW * warp + fr) * KP + fk;
+#pragma unroll
+      for (int kk = 0; kk < KCH; kk += 4) {
+        double av[QT];
+#pragma unroll
+        for (int i = 0; i < QT; ++i) av[i] = ap[8 * i * KP + kk];
+#pragma unroll
+        for (int q = 0; q < NTW; ++q) {
+          const double2 b = bp[8 * q * KP + kk];
+#pragma unroll
+          for (int i = 0; i < QT; ++i) {
+            dmma(cre[i][q], av[i], b.x);
+            dmma(cim[i][q], av[i], b.y);
+          }
+        }
+      }
+    }
+#pragma unroll
+    for (int q = 0; q < NTW; ++q)
+#pragma unroll
+      for (int u = 0; u < 2; ++u) {
+        const int rl = 8 * (NTW * warp + q) + 2 * fk + u;
+        const double2 ph = phr[r0 + rl];
+#pragma unroll
+        for (int i = 0; i < QT; ++i) {
+          const double ax = cre[i][q][u], ay = cim[i][q][u];
+          D1s[(8 * i + fr) * DP + rl] = make_double2(ax * ph.x - ay * ph.y, ax * ph.y + ay * ph.x);
+        }
+      }
+    __syncthreads();
+    // ---------------- stage 2: D[n][m] += sum_r a[n][r] D1[m][r]
+#pragma unroll
+    for (int s = 0; s < PPW; ++s) {
+      const int pi = warp + NW * s;
+      if (pi < QT * QT) {
+        const double* ap = a2s + (8 * (pi / QT) + fr) * DP + fk;
+        const double2* bp = D1s + (8 * (pi % QT) + fr) * DP + fk;
+#pragma unroll 8
+        for (int kk = 0; kk < RCH; kk += 4) {
+          const double av = ap[kk];
+          const double2 b = bp[kk];
+          dmma(d2re[s], av, b.x);
+          dmma(d2im[s], av, b.y);
+        }
+      }
+    }
+  }
+  __syncthreads();  // phase A is over: the region becomes Tsm | Ds | Hs
+#pragma unroll
+  for (int s = 0; s < PPW; ++s) {
+    const int pi = warp + NW * s;
+    if (pi < QT * QT) {
+#pragma unroll
+      for (int u = 0; u < 2; ++u) {
+        const int n = 8 * (pi / QT) + fr, m = 8 * (pi % QT) + 2 * fk + u;
+        Ds[n * QP + m] = rot_i(d2re[s][u], d2im[s][u], n + m);
+      }
+    }
+  }
+  for (int t = tid; t < G::JROWS * NQ; t += NT) Tsm[(t / NQ) * QP + t % NQ] = __ldg(ttab + t);
+  __syncthreads();
+  // ---------------- stage 3: H[n][jc] = sum_m D[n][m] T[jc][m], stored as Hs[jc][n]
+  for (int jt = warp; jt < G::JROWS / 8; jt += NW) {
+    double hre[QT][2], him[QT][2];
+#pragma unroll
+    for (int i = 0; i < QT; ++i) hre[i][0] = hre[i][1] = him[i][0] = him[i][1] = 0.0;
+#pragma unroll
+    for (int kk = 0; kk < NQ; kk += 4) {
+      const double b = Tsm[(8 * jt + fr) * QP + kk + fk];
+#pragma unroll
+      for (int i = 0; i < QT; ++i) {
+        const double2 a = Ds[(8 * i + fr) * QP + kk + fk];
+        dmma(hre[i], a.x, b);
+        dmma(him[i], a.y, b);
+      }
+    }
+#pragma unroll
+    for (int i = 0; i < QT; ++i)
+#pragma unroll
+      for (int u = 0; u < 2; ++u)
+        Hs[(8 * jt + 2 * fk + u) * QP + 8 * i + fr] = make_double2(hre[i][u], him[i][u]);
+  }
+  __syncthreads();
+  // ---------------- stage 4: G[jr][jc] = sum_n T[jr][n] H[n][jc]; running first-occurrence argmax
+  BestD best;
+  best.v = -1.0;
+  best.i = 0;
+  const int JT = (U + 7) / 8;
+  constexpr int GW = 5;  // window-column tiles per work unit (independent accumulation chains)
+  const int NG = (JT + GW - 1) / GW;
+  for (int un = warp; un < JT * NG; un += NW) {
+    const int jrt = un / NG, g0 = (un % NG) * GW;
+    double av[NQ / 4];
+#pragma unroll
+    for (int s = 0; s < NQ / 4; ++s) av[s] = Tsm[(8 * jrt + fr) * QP + 4 * s + fk];
+    double gre[GW][2], gim[GW][2];
+#pragma unroll
+    for (int w = 0; w < GW; ++w) gre[w][0] = gre[w][1] = gim[w][0] = gim[w][1] = 0.0;
+#pragma unroll
+    for (int s = 0; s < NQ / 4; ++s) {
+#pragma unroll
+      for (int w = 0; w < GW; ++w) {
+        const double2 b = Hs[(8 * (g0 + w) + fr) * QP + 4 * s + fk];  // tiles up to JROWS/8 exist
+        dmma(gre[w], av[s], b.x);
+        dmma(gim[w], av[s], b.y);
+      }
+    }
+#pragma unroll
+    for (int w = 0; w < GW; ++w)
+#pragma unroll
+      for (int u = 0; u < 2; ++u) {
+        const int jr = 8 * jrt + fr, jc = 8 * (g0 + w) + 2 * fk + u;
+        if (jr < U && jc < U)
+          bestd_take(best, gre[w][u] * gre[w][u] + gim[w][u] * gim[w][u], jr * U + jc);
+      }
+  }
+  return block_argmax<NW>(best, red, tid);
+}
+
 // MODE 0: far fields of two OBJECTS under an all-ones probe at the scan positions (ptycho.py:398-401)
 // MODE 1: src / target given in Fourier space [S,N,N] (register_translation_batch(space='fourier'))
 // MODE 2: src / target given in real space [S,N,N]    (space='real': fft2 of both first)
@@ -584,9 +824,12 @@ __global__ void __launch_bounds__(P::NT) k_register(const PassArgs a,
     if (sx > P::N / 2) sx -= P::N;
     double oy = (double)sy, ox = (double)sx;
     if (uf > 1) {
-      const int j = a.reg_mma
-                        ? register_refine_mma<P>(praw, a.reg_E, gemm, c.red, c.tid, sy, sx, U, uf, dftshift)
-                        : register_refine<P>(praw, a.reg_E, gemm, c.red, c.tid, sy, sx, U, uf, dftshift);
+      const int j =
+          a.reg_algo == 2
+              ? register_refine_cheb<P>(praw, a.reg_A, a.reg_T, smem_raw + G::OFF, c.red, c.tid, sy, sx, U)
+              : a.reg_algo == 1
+                    ? register_refine_mma<P>(praw, a.reg_E, gemm, c.red, c.tid, sy, sx, U, uf, dftshift)
+                    : register_refine<P>(praw, a.reg_E, gemm, c.red, c.tid, sy, sx, U, uf, dftshift);
       oy += (double)(j / U - dftshift) / (double)uf;
       ox += (double)(j % U - dftshift) / (double)uf;
     }

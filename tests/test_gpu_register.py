@@ -151,3 +151,37 @@ def test_cg_with_position_correction_vs_oracle(model):
     assert np.abs(d_scan.cpu().numpy() - scan_o).max() <= 0.0100001  # caller's scan mutated in place
     assert rel_l2(got["psi"].cpu().numpy(), want["psi"]) < 1e-4
     assert rel_l2(got["probe"].cpu().numpy(), want["probe"]) < 1e-4
+
+
+def test_register_algorithms_agree():
+    """The three forms of the upsampled matrix DFT -- low-rank Jacobi-Anger factorisation (default),
+    the reference's two direct matrix products on the FP64 tensor cores, and the same on the scalar
+    FP64 pipe -- must pick identical shifts (PTX_REG_ALGO is read once per process)."""
+    import json
+    import os
+    import subprocess
+    import sys
+    here = os.path.dirname(os.path.abspath(__file__))
+    code = (
+        "import sys, json, numpy as np, torch\n"
+        "sys.path[:0] = [%r, %r, %r]\n"
+        "import libtike.cufft as pt\n"
+        "from test_register_oracle import smooth_images, fourier_shift\n"
+        "out = {}\n"
+        "for N in (64, 128, 256):\n"
+        "    img = smooth_images(24, N, seed=N + 1)\n"
+        "    F = np.fft.fft2(img).astype(np.complex64)\n"
+        "    sh = np.random.default_rng(N).uniform(-5, 5, size=(24, 2))\n"
+        "    G = fourier_shift(F, sh)\n"
+        "    out[N] = pt.register_translation_batch(torch.from_numpy(F).cuda(), torch.from_numpy(G).cuda(),\n"
+        "                                           100, 'fourier').cpu().numpy().tolist()\n"
+        "print('RESULT' + json.dumps(out))\n" % (here, os.path.dirname(here),
+                                                   os.path.join(os.path.dirname(here), "libtike-cufft_b200")))
+    res = {}
+    for algo in ("lowrank", "dmma", "dfma"):
+        env = dict(os.environ, PTX_REG_ALGO=algo)
+        p = subprocess.run([sys.executable, "-c", code], env=env, capture_output=True, text=True, timeout=600)
+        assert p.returncode == 0, p.stderr[-2000:]
+        line = [ln for ln in p.stdout.splitlines() if ln.startswith("RESULT")][0]
+        res[algo] = json.loads(line[6:])
+    assert res["lowrank"] == res["dmma"] == res["dfma"]

@@ -36,5 +36,5 @@ for ndet in [int(x) for x in (sys.argv[1:] or ["128", "256"])]:
         ms = e0.elapsed_time(e1) / 5
     U = 150
     macs = S * (160 * ndet * ndet + 160 * 160 * ndet)
-    print("ndet %d: %.3f ms per %d patterns; %.2f TFLOP/s fp64 (8 flop per complex MAC, padded U'=160); "
+    print("ndet %d: %.3f ms per %d patterns; %.2f TFLOP/s fp64-equivalent of the direct products (8 flop per complex MAC, U=160); "
           "largest |shift| %.2f" % (ndet, ms, S, macs * 8 / ms / 1e9, float(out.abs().max())))
