@@ -446,6 +446,11 @@ def main():
                     help="angles per GPU per step (default: 8 for c2, 2 for c4 = 512 MiB of data)")
     ap.add_argument("--no-cg", action="store_true")
     args = ap.parse_args()
+    # stdout carries exactly ONE JSON line: anything libraries print on fd 1 meanwhile (NCCL's version
+    # banner, the solver's CSV header) goes to stderr instead
+    sys.stdout.flush()
+    json_fd = os.dup(1)
+    os.dup2(2, 1)
     args.warmup = max(args.warmup, 3)
     if args.angles <= 0:
         args.angles = 8 if args.workload == "c2" else 2
@@ -461,8 +466,10 @@ def main():
         if world > 1:
             import torch.distributed as dist
             dist.destroy_process_group()
+    sys.stdout.flush()
     if out is not None:
-        print(json.dumps(out))
+        os.write(json_fd, (json.dumps(out) + "\n").encode())
+    os.close(json_fd)
 
 
 if __name__ == "__main__":
