@@ -237,6 +237,12 @@ struct Plan<7> {
   using S2 = Stage<0, 2, 0, 2, 1, B128_3, W128_3>;
   static constexpr int RS = 148;  // 128 + max skew 7, = 4 mod 16
   static PTX_HD constexpr int skew(int x) { return x >> 4; }  // stage-2 lanes x4,x5 -> +1,+2
+  // The S1 <-> S2 exchange only moves data inside groups of 4 consecutive warps (S1 warps are
+  // (x5,x6,y5,y6), S2 warps (y3,y4,y5,y6): both have (y5,y6) on top; tests/emu_fft.cpp audits it
+  // when XG2 = 128), so a 128-thread named barrier could replace the block barrier there.  Measured
+  // on B200 (profiles/r01j_group_barrier.txt): fwd / adj +2.5 %, fused gradient +0 %, line search
+  // -8 % (the TMA-fed passes lose more from the drift than the butterflies gain) -> block barrier.
+  static constexpr int XG2 = 0;
 };
 
 // N = 64: 128 threads x 32 elements; x = 3+3 bits, y = 2+2+2 (last stage: radix-4 on y, 8 batches).
@@ -267,6 +273,7 @@ struct Plan<6> {
   using S2 = Stage<0, 0, 0, 2, 3, B64_3, W64_3>;
   static constexpr int RS = 68;
   static PTX_HD constexpr int skew(int x) { return (x >> 4) & 3; }
+  static constexpr int XG2 = 32;  // the S1 <-> S2 exchange stays inside a warp
 };
 
 // N = 256: cross radix 4 on y[7:6]; local tile 64 (y) x 256 (x): x = 3+3+2 bits, y = 2+2+2 bits.
@@ -293,6 +300,7 @@ struct Plan<8> {
   using S0 = Stage<5, 3, 4, 2, 0, NoBatch, WBIG_0>;
   using S1 = Stage<2, 3, 2, 2, 0, NoBatch, W256_1>;
   using S2 = Stage<0, 2, 0, 2, 1, B256_2, W256_2>;
+  static constexpr int XG2 = 0;   // S1 <-> S2 exchange spans the CTA: block barrier
   static constexpr int RS = 276;  // 256 + max skew 11, = 4 mod 16
   static PTX_HD constexpr int skew(int x) {  // stage-2 lanes x5,x6,x7 -> +1,+2,+8 (x2 gives +4)
     return ((x >> 5) & 3) + (((x >> 7) & 1) << 3);
@@ -320,6 +328,7 @@ struct Plan<9> {
   using S0 = Stage<5, 4, 4, 1, 0, NoBatch, WBIG_0>;
   using S1 = Stage<2, 3, 2, 2, 0, NoBatch, W512_1>;
   using S2 = Stage<0, 2, 0, 2, 1, B512_2, W512_2>;
+  static constexpr int XG2 = 0;
   static constexpr int RS = 532;  // 512 + max skew 15, = 4 mod 16
   static PTX_HD constexpr int skew(int x) { return (x >> 5) & 15; }  // stage-2 lanes x5..x8
 };

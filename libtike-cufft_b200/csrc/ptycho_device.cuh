@@ -322,6 +322,18 @@ __device__ __forceinline__ void gather_tma(float2 (&v)[P::E], Cta<P>& c, int cb,
     gather_tma_impl<P, false>(v, c, cb, shift, prb, g, p);
 }
 
+// barrier of the S1 <-> S2 exchange: only the XG2 threads that actually trade data (fft_tile.cuh)
+template <class P>
+__device__ __forceinline__ void xchg2_barrier(int tid) {
+  if (P::XG2 == 32) {
+    __syncwarp();
+  } else if (P::XG2 > 0) {
+    asm volatile("bar.sync %0, %1;" ::"r"(1 + tid / (P::XG2 > 0 ? P::XG2 : 1)), "n"(P::XG2 > 0 ? P::XG2 : 32) : "memory");
+  } else {
+    __syncthreads();
+  }
+}
+
 // ---------------------------------------------------------------- CTA-wide local transforms
 // forward: v (stage-0 ownership, natural order) -> v (stage-2 ownership, digit-reversed spectrum)
 template <class P>
@@ -337,7 +349,7 @@ __device__ __forceinline__ void fft_forward(float2 (&v)[P::E], float2* tile, con
   stage_load<typename P::S1, P>(v, tile, xf, yf);
   stage_compute<typename P::S1, false>(v, xf, yf, tw + TL::X1, tw + TL::Y1);
   stage_store<typename P::S1, P>(v, tile, xf, yf);
-  __syncthreads();
+  xchg2_barrier<P>(tid);
   fixed_coords<typename P::S2, P::WBITS>(tid, xf, yf);
   stage_load<typename P::S2, P>(v, tile, xf, yf);
   stage_compute<typename P::S2, false>(v, xf, yf, tw + TL::X2, tw + TL::Y2);
@@ -354,7 +366,7 @@ __device__ __forceinline__ void fft_inverse(float2 (&v)[P::E], float2* tile, con
   fixed_coords<typename P::S2, P::WBITS>(tid, xf, yf);
   stage_compute<typename P::S2, true>(v, xf, yf, tw + TL::X2, tw + TL::Y2);
   stage_store<typename P::S2, P>(v, tile, xf, yf);
-  __syncthreads();
+  xchg2_barrier<P>(tid);
   fixed_coords<typename P::S1, P::WBITS>(tid, xf, yf);
   stage_load<typename P::S1, P>(v, tile, xf, yf);
   stage_compute<typename P::S1, true>(v, xf, yf, tw + TL::X1, tw + TL::Y1);

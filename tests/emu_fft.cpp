@@ -221,6 +221,28 @@ static int check() {
   audit(typename P::S0{});
   audit(typename P::S1{});
   audit(typename P::S2{});
+  // ---- S1 <-> S2 exchange audit: every tile position is written and read inside one group of
+  // P::XG2 consecutive threads (0 = whole CTA), which is what lets fft_forward / fft_inverse use a
+  // group barrier there instead of a block barrier
+  int closed = 1;
+  if (P::XG2 > 0) {
+    std::vector<int> owner1(G::WORDS, -1);
+    for (int w = 0; w < NT; ++w)
+      for (int e = 0; e < E; ++e) {
+        int xf, yf, dx, dy;
+        fixed_coords<typename P::S1, P::WBITS>(w, xf, yf);
+        elem_offset<typename P::S1>(e, dx, dy);
+        owner1[G::idx(yf | dy, xf | dx)] = w / P::XG2;
+      }
+    for (int w = 0; w < NT; ++w)
+      for (int e = 0; e < E; ++e) {
+        int xf, yf, dx, dy;
+        fixed_coords<typename P::S2, P::WBITS>(w, xf, yf);
+        elem_offset<typename P::S2>(e, dx, dy);
+        if (owner1[G::idx(yf | dy, xf | dx)] != w / P::XG2) closed = 0;
+      }
+    if (!closed) printf("L=%d S1<->S2 exchange is NOT closed within groups of %d threads\n", L, P::XG2);
+  }
   // ---- spectrum coalescing audit: the 32 lanes of a warp must own 32 consecutive kx of one ky
   int coalesced = 1;
   for (int w0 = 0; w0 < NT; w0 += 32)
@@ -238,7 +260,7 @@ static int check() {
     }
   printf("L=%d N=%d fwd_rel_l2=%.3e inv_rel_l2=%.3e worst_bank_conflict=%d spectrum_coalesced=%d\n", L, N,
          efwd, einv, worst, coalesced);
-  return (efwd < 2e-6 && einv < 2e-6) ? 0 : 1;
+  return (efwd < 2e-6 && einv < 2e-6 && closed) ? 0 : 1;
 }
 
 int main() {
