@@ -254,7 +254,11 @@ static int launch(ptx_plan* p, int kid, PassArgs& a, cudaStream_t st) {
   }();
   const bool ls = (kid == K_LS_GAUSS || kid == K_LS_POIS);
   const bool inten = (kid == K_INT_GAUSS || kid == K_INT_POIS);
-  const bool want = policy == 2 || (policy == 1 && (ls || inten || (ops->RC > 1 && kid == K_FWD)));
+  // the object-gradient pass of the 64^2 plan gathers the NEXT pattern inside its scatter loop
+  // (scatter_gather_impl) with plain loads: no tensor map under any policy
+  const bool grad_obj1 = ops->N == 64 && (kid == K_GRAD_GAUSS_OBJ || kid == K_GRAD_POIS_OBJ);
+  const bool want = !grad_obj1 &&
+                    (policy == 2 || (policy == 1 && (ls || inten || (ops->RC > 1 && kid == K_FWD))));
   if (want && kid != K_NEAR && kid != K_ADJ_OBJ && kid != K_ADJ_PRB && !reg_kernel(kid) && a.psi) {
     const bool two = (kid == K_LS_GAUSS || kid == K_LS_POIS);
     if (make_object_map(p, a.psi, &tm_a) && (!two || make_object_map(p, a.psi_b, &tm_b))) a.use_tma = 1;

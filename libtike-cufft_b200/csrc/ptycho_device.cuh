@@ -614,6 +614,98 @@ __device__ __forceinline__ void scatter_impl(float2 (&v)[P::E], const Cta<P>& c,
   __syncthreads();
   tile_free();
 }
+// Scatter of the current pattern with the GATHER OF THE NEXT ONE folded into its loop (P == N, both
+// footprints inside the object).  Once t is parked in the tile the 32 registers of v are dead, and
+// the scatter loop -- two shared loads, a few FMAs and one fire-and-forget vector reduction per
+// output pixel -- leaves the load/store unit's global path idle: each of its 32 iterations also
+// fetches the four bilinear taps and the probe value of one near-plane pixel of pattern `pn`, whose
+// L2 latency (the whole cost of the stand-alone gather phase) hides under the scatter.  On return v
+// holds kappa * prb * patch(pn), ready for fft_forward.
+template <class P, class TileFree>
+__device__ __forceinline__ void scatter_gather_impl(float2 (&v)[P::E], const Cta<P>& c,
+                                                    const float2* __restrict__ prb, float scale,
+                                                    float2* __restrict__ grad_t,
+                                                    const float2* __restrict__ psi_next, const Geo& g,
+                                                    const Pat& p, const Pat& pn, TileFree tile_free) {
+  static_assert(P::RC == 1, "single-tile plans only");
+  constexpr int ROWS = P::N, COLS = P::N;
+  constexpr int PITCH = TileGeom<P>::WORDS / ROWS;
+  constexpr int RUN = ROWS * COLS / P::NT;
+  static_assert(RUN == P::E, "one gathered pixel per scatter iteration");
+  float2* tile = c.tile;
+  const float2 z = make_float2(0.f, 0.f);
+  __syncthreads();
+#pragma unroll
+  for (int e = 0; e < P::E; ++e) {
+    int y, x;
+    nat_coord<P>(c, 0, e, y, x);
+    const float2 pr = __ldg(prb + y * g.P + x);
+    float2 t;
+    t.x = scale * (pr.x * v[e].x + pr.y * v[e].y);
+    t.y = scale * (pr.x * v[e].y - pr.y * v[e].x);
+    tile[y * PITCH + 1 + x] = t;
+  }
+  if (c.tid < ROWS) tile[c.tid * PITCH] = z;
+  __syncthreads();
+  const int xl = c.tid % COLS, r0 = (c.tid / COLS) * RUN;
+  const int oc = p.C + xl;
+  const float a0 = 1.f - p.gam, a1 = p.gam, b0 = 1.f - p.rho, b1 = p.rho;
+  const float k00 = g.kappa * pn.w00, k01 = g.kappa * pn.w01, k10 = g.kappa * pn.w10, k11 = g.kappa * pn.w11;
+  {
+    const float2* tp = tile + r0 * PITCH + xl;
+    float2 hp = z;
+    if (r0 > 0) {
+      const float2 tl = tp[-PITCH], tc = tp[1 - PITCH];
+      hp = make_float2(a0 * tc.x + a1 * tl.x, a0 * tc.y + a1 * tl.y);
+    }
+    float2* dst = grad_t + (ptrdiff_t)(p.R + r0) * g.n + oc;
+    constexpr int CH = 4;  // gathered pixels in flight per thread (5 loads each): bounded register use
+#pragma unroll
+    for (int i0 = 0; i0 < RUN; i0 += CH) {
+      float2 f[CH][4], pr[CH];
+#pragma unroll
+      for (int j = 0; j < CH; ++j) {  // next pattern, near-plane pixels of registers i0 .. i0 + CH - 1
+        int y, x;
+        nat_coord<P>(c, 0, i0 + j, y, x);
+        const float2* q = psi_next + (size_t)(pn.R + y) * g.n + (pn.C + x);
+        f[j][0] = __ldg(q);
+        f[j][1] = __ldg(q + 1);
+        f[j][2] = __ldg(q + g.n);
+        f[j][3] = __ldg(q + g.n + 1);
+        pr[j] = __ldg(prb + y * g.P + x);
+      }
+#pragma unroll
+      for (int j = 0; j < CH; ++j) {  // this pattern, output rows r0 + i0 .. r0 + i0 + CH - 1
+        const int i = i0 + j;
+        const float2 tl = tp[i * PITCH], tc = tp[i * PITCH + 1];
+        const float2 hc = make_float2(a0 * tc.x + a1 * tl.x, a0 * tc.y + a1 * tl.y);
+        atomicAdd(dst + (ptrdiff_t)i * g.n, make_float2(b0 * hc.x + b1 * hp.x, b0 * hc.y + b1 * hp.y));
+        hp = hc;
+      }
+#pragma unroll
+      for (int j = 0; j < CH; ++j) {
+        float2 t;
+        t.x = f[j][0].x * k00 + f[j][1].x * k01 + f[j][2].x * k10 + f[j][3].x * k11;
+        t.y = f[j][0].y * k00 + f[j][1].y * k01 + f[j][2].y * k10 + f[j][3].y * k11;
+        v[i0 + j] = make_float2(pr[j].x * t.x - pr[j].y * t.y, pr[j].x * t.y + pr[j].y * t.x);
+      }
+      asm volatile("" ::: "memory");  // keep the next chunk's loads behind this chunk's arithmetic
+    }
+    if (r0 + RUN == ROWS)
+      atomicAdd(dst + (ptrdiff_t)RUN * g.n, make_float2(b1 * hp.x, b1 * hp.y));
+  }
+  if (c.tid < 32) {
+    const int oce = p.C + COLS;
+    for (int y = c.tid; y <= ROWS; y += 32) {
+      const float2 tc = y < ROWS ? tile[y * PITCH + COLS] : z;
+      const float2 tu = y > 0 ? tile[(y - 1) * PITCH + COLS] : z;
+      atomicAdd(grad_t + (ptrdiff_t)(p.R + y) * g.n + oce,
+                make_float2(a1 * (b0 * tc.x + b1 * tu.x), a1 * (b0 * tc.y + b1 * tu.y)));
+    }
+  }
+  __syncthreads();
+  tile_free();
+}
 // tile_free(): called by every thread once the tile is no longer needed (after a block barrier)
 template <class P, class TileFree>
 __device__ __forceinline__ void scatter_block(float2 (&v)[P::E], const Cta<P>& c, int cb,

@@ -352,6 +352,8 @@ __global__ void __launch_bounds__(P::NT) k_grad(const PassArgs a, const __grid_c
   int t_cur = -1;
   const int npat = g.T * g.S;
   if ((int)blockIdx.x < npat) dp_issue<P>(c, a.data + (size_t)blockIdx.x * P::N * P::N, 0);
+  float2 vv[P::E];    // near plane / spectrum of the pattern in flight (single-tile object pass)
+  bool have = false;  // vv already holds the gathered near plane of `pat`
   for (int pat = blockIdx.x; pat < npat; pat += gridDim.x) {
     const int t = pat / g.S;
     if (WHAT == 1 && t != t_cur) {
@@ -371,22 +373,47 @@ __global__ void __launch_bounds__(P::NT) k_grad(const PassArgs a, const __grid_c
     const float2* prb_t = a.prb + (size_t)t * a.prb_ts;
     float2* grad_t = a.grad + (size_t)t * g.nz * g.n;
     const float* ii = a.inten_in ? a.inten_in + (size_t)pat * P::N * P::N : nullptr;
+    auto residual = [&](int k1, float2(&v)[P::E]) {
+      dp_wait<P>(c);
+#pragma unroll
+      for (int e = 0; e < P::E; ++e) {
+        const float dd = c.dbuf[data_index<P>(c, e)];
+        const float I = ii ? __ldg(ii + spec_index<P>(c, k1, e)) * iscale
+                           : (v[e].x * v[e].x + v[e].y * v[e].y);
+        const float f = residual_factor<MODEL>(dd, I, fscale);
+        v[e].x *= f;
+        v[e].y *= f;
+      }
+    };
+    if constexpr (WHAT == 0 && P::N == 64) {
+      // object pass of the 64^2 plan: the next pattern's gather rides in this pattern's scatter
+      // loop (scatter_gather_impl) whenever both are plain full-window interior patterns.  Measured
+      // (profiles/r01j_scatter_gather.txt): +6 % at 64^2; at 128^2 the same fusion LOSES 6 % -- there
+      // both phases are bound by load/store-unit wavefronts, not by L2 latency, so nothing overlaps
+      // and the extra live registers cost spills -- hence 64^2 only.
+      if (!have) gather_nat<P>(vv, c, 0, psi_t, prb_t, g, p);
+      fft_forward<P>(vv, c.tile, c.tw, c.tid);
+      residual(0, vv);
+      fft_inverse<P>(vv, c.tile, c.tw, c.tid);
+      dp_next<P>(c, a.data, pat, 0, npat);
+      const int np = pat + (int)gridDim.x;
+      Pat pn;
+      pn.skip = true;
+      pn.inside = false;
+      if (np < npat) pn = make_pat(a.scan, np, g);
+      have = g.P == P::N && p.inside && np < npat && !pn.skip && pn.inside && (np / g.S) * (size_t)a.prb_ts == (size_t)t * a.prb_ts;
+      if (have)
+        scatter_gather_impl<P>(vv, c, prb_t, gscale, grad_t, a.psi + (size_t)(np / g.S) * g.nz * g.n, g, p, pn,
+                               []() {});
+      else
+        scatter_block<P>(vv, c, 0, prb_t, gscale, grad_t, g, p, []() {});
+      continue;
+    }
     fused_pass<P>(
         c, [&](int cb, float2(&v)[P::E]) {
           gather_any<P>(v, c, cb, a.use_tma, &tm_a, 2 * pat, t, psi_t, prb_t, g, p);
         },
-        [&](int k1, float2(&v)[P::E]) {
-          dp_wait<P>(c);
-#pragma unroll
-          for (int e = 0; e < P::E; ++e) {
-            const float dd = c.dbuf[data_index<P>(c, e)];
-            const float I = ii ? __ldg(ii + spec_index<P>(c, k1, e)) * iscale
-                               : (v[e].x * v[e].x + v[e].y * v[e].y);
-            const float f = residual_factor<MODEL>(dd, I, fscale);
-            v[e].x *= f;
-            v[e].y *= f;
-          }
-        },
+        residual,
         [&](int k1) {
           dp_next<P>(c, a.data, pat, k1, npat);
           if (WHAT == 1 && P::RC == 1 && Patch<P>::TMA && a.use_tma) {  // probe pass: the tile is idle after the inverse
