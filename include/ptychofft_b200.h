@@ -150,6 +150,17 @@ int ptx_cg_position_shifts(ptx_plan* p, const void* psi_a, const void* psi_b, co
                            int upsample_factor, double* shifts, void* stream);
 
 /* ---------------------------------------------------------------------------------------
+ * Data preparation in front of the solver (the reference's catalyst driver,
+ * tests/catalyst/test_rec_script.py:44-46, 98-100, 209; ":43 TODO ... moved to compute kernels").
+ * ------------------------------------------------------------------------------------- */
+
+/* out[s][y][x] = raw[ids[s]][(y + n/2) % n][(x + n/2) % n] / denominator, s < nsel: frame selection
+ * (ids == NULL: frame s), fftshift (when fftshift != 0) and normalisation in one HBM pass.
+ * raw: [*, n, n] float32 device array, ids: nsel int64 on the device, out: [nsel, n, n]. */
+int ptx_prepare_data(const float* raw, const long long* ids, size_t nsel, size_t n, float denominator,
+                     int fftshift, float* out, void* stream);
+
+/* ---------------------------------------------------------------------------------------
  * Small fused vector kernels on object / probe sized complex arrays (n complex elements),
  * replacing the CuPy temporaries of ptycho.py:344, 356, 366-372, 405, 435, 444-450, 463.
  * ------------------------------------------------------------------------------------- */

@@ -125,6 +125,27 @@ __global__ void k_absmax(const float2* __restrict__ x, size_t n, float* out) {
   if ((threadIdx.x & 31) == 0) atomicMax(reinterpret_cast<int*>(out), __float_as_int(sqrtf(m)));
 }
 
+
+// out[s][y][x] = in[ids[s]][(y + N/2) % N][(x + N/2) % N] / den : frame selection + fftshift +
+// normalisation of the measured data in one pass (tests/catalyst/test_rec_script.py:44-46, 98-100, 209)
+__global__ void k_prepare_data(const float* __restrict__ in, const long long* __restrict__ ids, size_t nsel,
+                               int N, float den, int shift, float* __restrict__ out) {
+  const int h = shift ? N / 2 : 0;
+  const size_t total = nsel * (size_t)N * (size_t)(N / 4);
+  for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < total;
+       i += (size_t)gridDim.x * blockDim.x) {
+    const int x4 = (int)(i % (N / 4)) * 4;
+    const int y = (int)((i / (N / 4)) % N);
+    const size_t s = i / ((size_t)N * (N / 4));
+    const size_t f = ids ? (size_t)ids[s] : s;
+    int ys = y + h, xs = x4 + h;
+    if (ys >= N) ys -= N;
+    if (xs >= N) xs -= N;  // N/2 is a multiple of 4: the four source pixels stay contiguous
+    const float4 v = __ldg(reinterpret_cast<const float4*>(in + (f * N + ys) * N + xs));
+    *reinterpret_cast<float4*>(out + (s * N + y) * N + x4) = make_float4(v.x / den, v.y / den, v.z / den, v.w / den);
+  }
+}
+
 }  // namespace ptx
 
 // ==========================================================================================
@@ -683,6 +704,20 @@ int ptx_cg_position_shifts(ptx_plan* p, const void* psi_a, const void* psi_b, co
   a.reg_T = p->reg_AT ? p->reg_AT + (size_t)REG_NQ * p->ndet : nullptr;
   a.reg_algo = reg_algo();
   return launch(p, K_REG_OBJ, a, st);
+}
+
+int ptx_prepare_data(const float* raw, const long long* ids, size_t nsel, size_t n, float denominator,
+                     int fftshift, float* out, void* stream) {
+  if (!raw || !out || !nsel) return fail(PTX_EINVAL, "ptx_prepare_data: bad argument");
+  if (n < 8 || n % 8) return fail(PTX_EINVAL, "ptx_prepare_data: frame size must be a multiple of 8");
+  if (((uintptr_t)raw | (uintptr_t)out) & 15) return fail(PTX_EINVAL, "ptx_prepare_data: arrays must be 16-byte aligned");
+  const size_t total = nsel * n * (n / 4);
+  size_t b = (total + 255) / 256;
+  const int grid = (int)(b > 148 * 16 ? 148 * 16 : b);
+  k_prepare_data<<<grid, 256, 0, (cudaStream_t)stream>>>(raw, ids, nsel, (int)n, denominator, fftshift, out);
+  g_launches.fetch_add(1);
+  CUDA_TRY(cudaGetLastError());
+  return PTX_OK;
 }
 
 static int vec_grid(size_t n) {

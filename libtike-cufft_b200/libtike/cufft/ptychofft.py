@@ -41,6 +41,7 @@ SYMBOLS = [
                                _i, _dp, _vp]),
     ("ptx_register_translation", _i, [_vp, _vp, _vp, _sz, _i, _i, _dp, _vp]),
     ("ptx_cg_position_shifts", _i, [_vp, _vp, _vp, _vp, _i, _dp, _vp]),
+    ("ptx_prepare_data", _i, [_fp, _vp, _sz, _sz, ctypes.c_float, _i, _fp, _vp]),
     ("ptx_vec_dai_yuan_reduce", _i, [_vp, _vp, _vp, _sz, _dp, _vp]),
     ("ptx_vec_dai_yuan_update", _i, [_vp, _vp, _vp, _sz, _dp, _i, _vp]),
     ("ptx_vec_axpy", _i, [_vp, _vp, _sz, _fp, _vp]),

@@ -275,8 +275,10 @@ def test_cg_cost_decreases_c2():
 
 
 @pytest.mark.skipif(not ref_gpu.available(), reason="oracle/_ref not built")
-@pytest.mark.parametrize("ndet,nprb,model", [(128, 96, "gaussian"), (64, 64, "poisson"), (256, 256, "gaussian")])
-def test_cg_skipped_positions_window_and_two_angles(ndet, nprb, model):
+@pytest.mark.parametrize("ndet,nprb,model,poscorr", [(128, 96, "gaussian", False), (64, 64, "poisson", False),
+                                                     (256, 256, "gaussian", False), (64, 64, "poisson", True),
+                                                     (128, 96, "gaussian", True)])
+def test_cg_skipped_positions_window_and_two_angles(ndet, nprb, model, poscorr):
     """Edge cases of the solver against the reference's cuFFT path: positions flagged -1 (skipped,
     tests/test_fsc.py:16-17) including the first and the last pattern of the batch, a probe window
     smaller than the detector, and ptheta = 2 (CG scalars global over both angles)."""
@@ -295,17 +297,27 @@ def test_cg_skipped_positions_window_and_two_angles(ndet, nprb, model):
     prb0 = (probe * (0.9 + 0.1j)).astype(np.complex64)
     piter = 3
     with ref_gpu.RefCGPtychoSolver(S, nprb, ndet, T, nz, n) as ref:
+        ref.position_correction = poscorr  # ON: angle 0 only, skipped positions get -0.75 (still < 0)
+        ref.shift_log = []
         want = ref.run_batch(data, psi0, scan, prb0, piter=piter, model=model, recover_prb=True,
                              verbose=False)
         steps = [t[2] for t in ref.last_trials]
+        rlog = ref.shift_log
 
     def exact():
         with O.float64_arithmetic():
-            return O.cg_run(data, psi0, scan, prb0.copy(), piter, model, True, ndet=ndet,
-                            forced_steps=list(steps))
+            return O.cg_run(data, psi0, scan.copy(), prb0.copy(), piter, model, True, ndet=ndet,
+                            forced_steps=list(steps), position_correction=poscorr)
 
     with pt.CGPtychoSolver(S, nprb, ndet, T, nz, n) as slv:
+        slv.position_correction = poscorr
         slv._forced_steps = list(steps)
         got = slv.run_batch(data, psi0, scan, prb0, piter=piter, model=model, recover_prb=True)
-        same = _assert_parity(got, want, exact, "(skips, window, ptheta=2) %s" % ((ndet, nprb, model),))
+        same = _assert_parity(got, want, exact, "(skips, window, ptheta=2) %s" % ((ndet, nprb, model, poscorr),))
         _audit_decisions(slv, steps, strict=same)
+        if poscorr:
+            glog = [x.cpu().numpy() for x in slv.shift_log]
+            assert len(glog) == len(rlog) == piter - 1 and glog[0].shape == (S, 2)
+            for a, b in zip(glog, rlog):
+                assert np.array_equal(a[0], [-0.75, -0.75]) and np.array_equal(b[0], [-0.75, -0.75])
+                assert np.abs(a - b).max() <= 0.0100001

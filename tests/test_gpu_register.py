@@ -185,3 +185,37 @@ def test_register_algorithms_agree():
         line = [ln for ln in p.stdout.splitlines() if ln.startswith("RESULT")][0]
         res[algo] = json.loads(line[6:])
     assert res["lowrank"] == res["dmma"] == res["dfma"]
+
+
+@pytest.mark.skipif(not ref_gpu.available(), reason="oracle/_ref not built")
+def test_c2_full_size_position_correction_vs_reference():
+    """BASELINE.json configs[1] at full size (1024 positions, 128^2 detector, 512^2 object): three CG
+    iterations exactly as the reference executes them (position correction on) against the
+    reference's cuFFT operators + restated solver on the same GPU."""
+    pt = _pt()
+    w = workloads.c2_single_angle() if hasattr(workloads, "c2_single_angle") else None
+    if w is None:
+        w = workloads.synth_angles(1, 512, 512, 128, 128, 32, 1, seed0=0)
+    psi, scan, probe = w["psi"], w["scan"], w["probe"]
+    S = scan.shape[1]
+    data = (np.abs(O.fwd(psi, scan, np.ascontiguousarray(probe[:, 0]), 128)) ** 2).astype(np.float32)
+    init = np.ones_like(psi)
+    prb0 = (probe * (0.9 + 0.1j)).astype(np.complex64)
+    with ref_gpu.RefCGPtychoSolver(S, 128, 128, 1, 512, 512) as ref:
+        ref.position_correction = True
+        ref.shift_log = []
+        want = ref.run_batch(data, init, scan, prb0, piter=3, model="gaussian", recover_prb=True,
+                             verbose=False)
+        steps = [t[2] for t in ref.last_trials]
+        rlog = ref.shift_log
+    with pt.CGPtychoSolver(S, 128, 128, 1, 512, 512) as slv:
+        slv._forced_steps = list(steps)
+        got = slv.run_batch(data, init, scan, prb0, piter=3, model="gaussian", recover_prb=True)
+        glog = [x.cpu().numpy() for x in slv.shift_log]
+    nbad = sum(int((np.abs(a - b).max(axis=1) > 0).sum()) for a, b in zip(glog, rlog))
+    worst = max(float(np.abs(a - b).max()) for a, b in zip(glog, rlog))
+    print("c2 full size: %d of %d shifts differ (worst %.3f px, largest shift %.2f px); psi %.2e probe %.2e"
+          % (nbad, S * len(rlog), worst, max(float(np.abs(b).max()) for b in rlog),
+             rel_l2(got["psi"], want["psi"]), rel_l2(got["probe"], want["probe"])))
+    assert worst <= 0.0100001 and nbad <= S * len(rlog) // 50
+    assert rel_l2(got["psi"], want["psi"]) < 1e-4 and rel_l2(got["probe"], want["probe"]) < 1e-4

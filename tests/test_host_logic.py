@@ -71,6 +71,13 @@ def test_reference_import_surface(built):
         ["ptheta", "nz", "n", "nscan", "detector_shape", "probe_shape"]
     assert list(inspect.signature(CGPtychoSolver.run).parameters)[1:] == \
         ["data", "psi", "scan", "probe", "piter", "model", "recover_prb", "ortho_prb"]
+    # module-level registration function of the reference (ptycho.py:192-193) and its defaults
+    assert list(inspect.signature(pt.register_translation_batch).parameters) == \
+        ["src_image", "target_image", "upsample_factor", "space"]
+    sig = inspect.signature(pt.register_translation_batch)
+    assert sig.parameters["upsample_factor"].default == 1 and sig.parameters["space"].default == "real"
+    # the reference runs its position-correction block unconditionally (ptycho.py:398-403)
+    assert CGPtychoSolver.position_correction is True and CGPtychoSolver.position_upsample == 100
 
 
 def test_line_search_sqr_matches_reference_semantics(built):
