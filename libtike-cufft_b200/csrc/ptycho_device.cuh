@@ -148,18 +148,22 @@ __device__ __forceinline__ void dp_issue(const Cta<P>& c, const float* d_pat, in
     asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(TOTAL));
   }
   __syncwarp();
+  // the measured data are read exactly once per pass: evict-first in L2, so that the stream does
+  // not push out what IS reused there (object, probe, and the scratch frames of the N > 128 plans)
+  unsigned long long pol;
+  asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(pol));
   if (P::RC == 1) {
     if (c.tid == 0)
       asm volatile(
-          "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::
-              "r"(smem_u32(c.dbuf)), "l"(d_pat), "r"(TOTAL), "r"(bar)
+          "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint [%0], [%1], %2, [%3], %4;" ::
+              "r"(smem_u32(c.dbuf)), "l"(d_pat), "r"(TOTAL), "r"(bar), "l"(pol)
           : "memory");
   } else {  // rows ky = k1 + RC * j of the N x N data frame, one bulk copy per row
     for (int j = c.tid; j < P::NY; j += 32)
       asm volatile(
-          "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::
+          "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint [%0], [%1], %2, [%3], %4;" ::
               "r"(smem_u32(c.dbuf + j * P::N)), "l"(d_pat + (size_t)(k1 + P::RC * j) * P::N),
-              "r"((unsigned)(P::N * 4)), "r"(bar)
+              "r"((unsigned)(P::N * 4)), "r"(bar), "l"(pol)
           : "memory");
   }
 }
