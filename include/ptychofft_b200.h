@@ -110,21 +110,25 @@ int ptx_cg_intensity(ptx_plan* p, const void* psi, const void* scan, const void*
  *   r = F*fscale * (1 - data/(I+1e-32))                  poisson
  *   what 0: grad_out[T,nz,n] += gscale * adj(r, scan, probe[:,mode])
  *   what 1: grad_out[t*grad_angle_stride + (P,P)] += gscale * adj_probe(r, scan, psi)
- * sc: 3 device floats {fscale, iscale, gscale}.  grad_out accumulates (caller zeroes it). */
+ * sc: 3 device floats {fscale, iscale, gscale}.  grad_out accumulates (caller zeroes it).
+ * far_out (nullable): [T,S,N,N] c64, receives F itself (before the residual), for the line search
+ * that follows -- re-reading 8 N^2 bytes is cheaper than gathering and transforming again. */
 int ptx_cg_grad(ptx_plan* p, int what, const void* psi, const void* scan, const void* probe,
                 int nmodes, int mode, const float* data, const float* inten_in, const float* sc,
-                int model, void* grad_out, size_t grad_angle_stride, void* stream);
+                int model, void* grad_out, size_t grad_angle_stride, void* far_out, void* stream);
 
 /* ptycho.py:383-393 (object, npairs = nmodes) and 451-461 (probe, npairs = 1):
  *   for each pair j: t1 = fwd(obj_a, prb_a[:,ja]) ; t2 = fwd(obj_b, prb_b[:,jb])
  *   p1 += |t1|^2 ; p2 += |t2|^2 ; p3 += 2 Re(t1 conj t2)      (p1 = p1_in when given)
  *   cost[0] += minf(p1) ; cost[1+c] += minf(p1 + g^2 p2 + g p3), g = 2^-(c0+c), c < 4
  * Pair j uses modes (mode_a0 + j, mode_b0 + j).  The kernel always evaluates four candidates per
- * pass (ncand <= 4 tells how many the caller will look at).  cost: 9 doubles, caller-zeroed. */
+ * pass (ncand <= 4 tells how many the caller will look at).  cost: 9 doubles, caller-zeroed.
+ * far_a (nullable): [npairs][T,S,N,N] c64 -- t1 of every pair as left by ptx_cg_grad(far_out); when
+ * given, obj_a / prb_a are not transformed again (skipped positions read as 0). */
 int ptx_cg_linesearch(ptx_plan* p, const void* obj_a, const void* prb_a, int nmodes_a, int mode_a0,
                       const void* obj_b, const void* prb_b, int nmodes_b, int mode_b0, int npairs,
-                      const void* scan, const float* data, const float* p1_in, int model, int c0,
-                      int ncand, double* cost, void* stream);
+                      const void* scan, const float* data, const float* p1_in, const void* far_a,
+                      int model, int c0, int ncand, double* cost, void* stream);
 
 /* ---------------------------------------------------------------------------------------
  * Position correction (ptycho.py:163-248, called from the CG loop at ptycho.py:398-403).

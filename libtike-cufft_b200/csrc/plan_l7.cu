@@ -1,6 +1,18 @@
-// Kernel family for detector size 2^7 (see ptycho_passes.cuh); one translation unit per size.
-#include "ptycho_register.cuh"
+// Kernel family for detector size 2^7, part 1 of 3: operators, intensity pass, and the table itself.
+#include "ptycho_table.cuh"
 
 namespace ptx {
-const PlanOps* ops_l7() { return make_ops<Plan<7>>(); }
+void fill_grad_l7(PlanOps& ops);    // plan_l7_grad.cu
+void fill_search_l7(PlanOps& ops);  // plan_l7_search.cu
+const PlanOps* ops_l7() {
+  static PlanOps ops;
+  static bool init = false;
+  if (!init) {
+    fill_ops_base<Plan<7>>(ops);
+    fill_grad_l7(ops);
+    fill_search_l7(ops);
+    init = true;
+  }
+  return &ops;
+}
 }  // namespace ptx

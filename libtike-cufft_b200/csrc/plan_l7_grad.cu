@@ -1,0 +1,6 @@
+// Kernel family for detector size 2^7, part 2 of 3: the fused gradient kernels (ptycho_passes.cuh).
+#include "ptycho_table.cuh"
+
+namespace ptx {
+void fill_grad_l7(PlanOps& ops) { fill_ops_grad<Plan<7>>(ops); }
+}  // namespace ptx

@@ -1,0 +1,6 @@
+// Kernel family for detector size 2^7, part 3 of 3: line search and position correction.
+#include "ptycho_table.cuh"
+
+namespace ptx {
+void fill_search_l7(PlanOps& ops) { fill_ops_search<Plan<7>>(ops); }
+}  // namespace ptx

@@ -1,6 +1,18 @@
-// Kernel family for detector size 2^8 (see ptycho_passes.cuh); one translation unit per size.
-#include "ptycho_register.cuh"
+// Kernel family for detector size 2^8, part 1 of 3: operators, intensity pass, and the table itself.
+#include "ptycho_table.cuh"
 
 namespace ptx {
-const PlanOps* ops_l8() { return make_ops<Plan<8>>(); }
+void fill_grad_l8(PlanOps& ops);    // plan_l8_grad.cu
+void fill_search_l8(PlanOps& ops);  // plan_l8_search.cu
+const PlanOps* ops_l8() {
+  static PlanOps ops;
+  static bool init = false;
+  if (!init) {
+    fill_ops_base<Plan<8>>(ops);
+    fill_grad_l8(ops);
+    fill_search_l8(ops);
+    init = true;
+  }
+  return &ops;
+}
 }  // namespace ptx

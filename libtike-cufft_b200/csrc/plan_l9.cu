@@ -1,6 +1,18 @@
-// Kernel family for detector size 2^9 (see ptycho_passes.cuh); one translation unit per size.
-#include "ptycho_register.cuh"
+// Kernel family for detector size 2^9, part 1 of 3: operators, intensity pass, and the table itself.
+#include "ptycho_table.cuh"
 
 namespace ptx {
-const PlanOps* ops_l9() { return make_ops<Plan<9>>(); }
+void fill_grad_l9(PlanOps& ops);    // plan_l9_grad.cu
+void fill_search_l9(PlanOps& ops);  // plan_l9_search.cu
+const PlanOps* ops_l9() {
+  static PlanOps ops;
+  static bool init = false;
+  if (!init) {
+    fill_ops_base<Plan<9>>(ops);
+    fill_grad_l9(ops);
+    fill_search_l9(ops);
+    init = true;
+  }
+  return &ops;
+}
 }  // namespace ptx

@@ -277,7 +277,8 @@ static int launch(ptx_plan* p, int kid, PassArgs& a, cudaStream_t st) {
   const bool inten = (kid == K_INT_GAUSS || kid == K_INT_POIS);
   // the object-gradient pass of the 64^2 plan gathers the NEXT pattern inside its scatter loop
   // (scatter_gather_impl) with plain loads: no tensor map under any policy
-  const bool grad_obj1 = ops->N == 64 && (kid == K_GRAD_GAUSS_OBJ || kid == K_GRAD_POIS_OBJ);
+  const bool grad_obj1 = ops->N == 64 && (kid == K_GRAD_GAUSS_OBJ || kid == K_GRAD_POIS_OBJ ||
+                                          kid == K_GRADC_GAUSS_OBJ || kid == K_GRADC_POIS_OBJ);
   const bool want = !grad_obj1 &&
                     (policy == 2 || (policy == 1 && (ls || inten || (ops->RC > 1 && kid == K_FWD))));
   if (want && kid != K_NEAR && kid != K_ADJ_OBJ && kid != K_ADJ_PRB && !reg_kernel(kid) && a.psi) {
@@ -502,7 +503,7 @@ int ptx_cg_intensity(ptx_plan* p, const void* psi, const void* scan, const void*
 
 int ptx_cg_grad(ptx_plan* p, int what, const void* psi, const void* scan, const void* probe,
                 int nmodes, int mode, const float* data, const float* inten_in, const float* sc,
-                int model, void* grad_out, size_t grad_angle_stride, void* stream) {
+                int model, void* grad_out, size_t grad_angle_stride, void* far_out, void* stream) {
   int rc = check_plan(p);
   if (rc) return rc;
   if (!psi || !scan || !probe || !data || !sc || !grad_out || nmodes < 1 || mode < 0 ||
@@ -519,18 +520,21 @@ int ptx_cg_grad(ptx_plan* p, int what, const void* psi, const void* scan, const 
   a.sc = sc;
   a.grad = (float2*)grad_out;
   a.grad_ts = grad_angle_stride ? grad_angle_stride : pp;
+  a.far = (float2*)far_out;
   cudaStream_t st = (cudaStream_t)stream;
   if (model == PTX_MODEL_GAUSSIAN)
-    return launch(p, what == 0 ? K_GRAD_GAUSS_OBJ : K_GRAD_GAUSS_PRB, a, st);
+    return launch(p, far_out ? (what == 0 ? K_GRADC_GAUSS_OBJ : K_GRADC_GAUSS_PRB)
+                             : (what == 0 ? K_GRAD_GAUSS_OBJ : K_GRAD_GAUSS_PRB), a, st);
   if (model == PTX_MODEL_POISSON)
-    return launch(p, what == 0 ? K_GRAD_POIS_OBJ : K_GRAD_POIS_PRB, a, st);
+    return launch(p, far_out ? (what == 0 ? K_GRADC_POIS_OBJ : K_GRADC_POIS_PRB)
+                             : (what == 0 ? K_GRAD_POIS_OBJ : K_GRAD_POIS_PRB), a, st);
   return fail(PTX_EINVAL, "unknown model %d", model);
 }
 
 int ptx_cg_linesearch(ptx_plan* p, const void* obj_a, const void* prb_a, int nmodes_a, int mode_a0,
                       const void* obj_b, const void* prb_b, int nmodes_b, int mode_b0, int npairs,
-                      const void* scan, const float* data, const float* p1_in, int model, int c0,
-                      int ncand, double* cost, void* stream) {
+                      const void* scan, const float* data, const float* p1_in, const void* far_a,
+                      int model, int c0, int ncand, double* cost, void* stream) {
   int rc = check_plan(p);
   if (rc) return rc;
   if (!obj_a || !prb_a || !obj_b || !prb_b || !scan || !data || !cost || npairs < 1 || ncand < 1 ||
@@ -550,6 +554,8 @@ int ptx_cg_linesearch(ptx_plan* p, const void* obj_a, const void* prb_a, int nmo
   a.scan = (const float2*)scan;
   a.data = data;
   a.inten_in = p1_in;
+  a.far_in = (const float2*)far_a;
+  a.far_ms = p->ptheta * p->nscan * p->ndet * p->ndet;
   a.npairs = npairs;
   a.c0 = c0;
   a.ncand = ncand;

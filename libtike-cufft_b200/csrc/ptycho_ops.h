@@ -32,8 +32,9 @@ struct PassArgs {
   const float* data;        // [T,S,N,N]
   const float* inten_in;    // [T,S,N,N] or null
   float* inten_out;         // [T,S,N,N] or null
-  float2* far;              // [T,S,N,N]
-  const float2* far_in;
+  float2* far;              // [T,S,N,N] (k_fwd output; k_grad: optional far-field cache, pre-residual)
+  const float2* far_in;     // k_adj input; k_linesearch: optional cached first far field of every pair
+  size_t far_ms;            // complex elements between modes (pairs) of the cache
   float2* grad;  // object gradient [T,nz,n] or probe gradient base (angle stride grad_ts)
   size_t grad_ts;
   const float* sc;  // device scalars
@@ -53,6 +54,7 @@ enum KernelId {
   K_FWD = 0, K_NEAR, K_ADJ_OBJ, K_ADJ_PRB, K_INT_GAUSS, K_INT_POIS,
   K_GRAD_GAUSS_OBJ, K_GRAD_GAUSS_PRB, K_GRAD_POIS_OBJ, K_GRAD_POIS_PRB, K_LS_GAUSS, K_LS_POIS,
   K_REG_OBJ, K_REG_FOURIER, K_REG_REAL,
+  K_GRADC_GAUSS_OBJ, K_GRADC_GAUSS_PRB, K_GRADC_POIS_OBJ, K_GRADC_POIS_PRB,  // + far-field cache output
   K_COUNT
 };
 

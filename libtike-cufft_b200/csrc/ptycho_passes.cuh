@@ -340,7 +340,7 @@ __global__ void __launch_bounds__(P::NT) k_intensity(const PassArgs a,
 //   ptycho.py:347-363 (object), 421-441 (probe)
 // sc = {fscale, iscale, gscale}
 // ------------------------------------------------------------------------------------------
-template <class P, int MODEL, int WHAT>
+template <class P, int MODEL, int WHAT, bool CACHE>
 __global__ void __launch_bounds__(P::NT) k_grad(const PassArgs a, const __grid_constant__ CUtensorMap tm_a,
                                                 const __grid_constant__ CUtensorMap tm_b) {
   extern __shared__ __align__(128) unsigned char smem_raw[];
@@ -373,7 +373,12 @@ __global__ void __launch_bounds__(P::NT) k_grad(const PassArgs a, const __grid_c
     const float2* prb_t = a.prb + (size_t)t * a.prb_ts;
     float2* grad_t = a.grad + (size_t)t * g.nz * g.n;
     const float* ii = a.inten_in ? a.inten_in + (size_t)pat * P::N * P::N : nullptr;
+    float2* fc = CACHE ? a.far + (size_t)pat * P::N * P::N : nullptr;
     auto residual = [&](int k1, float2(&v)[P::E]) {
+      if (CACHE) {  // keep F(psi, probe) for the line search that follows (ptycho.py:385, 457): 8 N^2 B
+#pragma unroll
+        for (int e = 0; e < P::E; ++e) __stcg(fc + spec_index<P>(c, k1, e), v[e]);
+      }
       dp_wait<P>(c);
 #pragma unroll
       for (int e = 0; e < P::E; ++e) {
@@ -463,18 +468,22 @@ __global__ void __launch_bounds__(P::NT) k_linesearch(const PassArgs a,
       const float2* prb_a = a.prb + (size_t)t * a.prb_ts + (size_t)j * a.prb_ms;
       const float2* prb_b = a.prb_b + (size_t)t * a.prb_b_ts + (size_t)j * a.prb_b_ms;
       const bool first = (j == 0), last = (j + 1 == a.npairs);
-      spectrum_pass<P>(
-          c, p.skip, [&](int cb, float2(&v)[P::E]) {
-            gather_any<P>(v, c, cb, a.use_tma, &tm_a, 2 * pat, t, psi_a, prb_a, g, p);
-          },
-          [&](int k1, float2(&v)[P::E]) {
-            float2* st = c.stash + (size_t)k1 * P::E * P::NT + c.tid;
+      // the pair's first far field was left in HBM by the gradient pass that preceded this search
+      // (reading 8 N^2 bytes costs a quarter of recomputing gather + transform)
+      const float2* t1c = a.far_in ? a.far_in + (size_t)j * a.far_ms + (size_t)pat * NN : nullptr;
+      if (!t1c)
+        spectrum_pass<P>(
+            c, p.skip, [&](int cb, float2(&v)[P::E]) {
+              gather_any<P>(v, c, cb, a.use_tma, &tm_a, 2 * pat, t, psi_a, prb_a, g, p);
+            },
+            [&](int k1, float2(&v)[P::E]) {
+              float2* st = c.stash + (size_t)k1 * P::E * P::NT + c.tid;
 #pragma unroll
-            for (int e = 0; e < P::E; ++e) st[e * P::NT] = v[e];
-          },
-          [&](int k1) {  // the second object's patch of the same pattern comes next
-            if (k1 == P::RC - 1) patch_prefetch<P>(c, a.use_tma, &tm_b, 2 * pat + 1, pat, npat, a.scan, g);
-          });
+              for (int e = 0; e < P::E; ++e) st[e * P::NT] = v[e];
+            },
+            [&](int k1) {  // the second object's patch of the same pattern comes next
+              if (k1 == P::RC - 1) patch_prefetch<P>(c, a.use_tma, &tm_b, 2 * pat + 1, pat, npat, a.scan, g);
+            });
       spectrum_pass<P>(
           c, p.skip, [&](int cb, float2(&v)[P::E]) {
             gather_any<P>(v, c, cb, a.use_tma, &tm_b, 2 * pat + 1, t, psi_b, prb_b, g, p);
@@ -485,10 +494,19 @@ __global__ void __launch_bounds__(P::NT) k_linesearch(const PassArgs a,
             float cost[5];  // fp32 over 32 pixels, double across tiles
 #pragma unroll
             for (int q = 0; q < 5; ++q) cost[q] = 0.f;
+            const float2* t1p = (t1c && !p.skip) ? t1c + c.sbase + k1 * P::N : nullptr;
             if (last) dp_wait<P>(c);
 #pragma unroll
             for (int e = 0; e < P::E; ++e) {
-              const float2 t1 = st[e * P::NT];
+              float2 t1;
+              if (t1c) {  // block-uniform
+                int dx, dy;
+                elem_offset<typename P::S2>(e, dx, dy);
+                t1 = t1p ? __ldcg(t1p + (P::RC * pos_to_freq_y<P>(dy) * P::N + pos_to_freq_x<P>(dx)))
+                         : make_float2(0.f, 0.f);
+              } else {
+                t1 = st[e * P::NT];
+              }
               const float2 t2 = v[e];
               float q1 = t1.x * t1.x + t1.y * t1.y;
               float q2 = t2.x * t2.x + t2.y * t2.y;
@@ -525,9 +543,12 @@ __global__ void __launch_bounds__(P::NT) k_linesearch(const PassArgs a,
           },
           [&](int k1) {
             if (last) dp_next<P>(c, a.data, pat, k1, npat);
-            if (k1 == P::RC - 1) {  // next pair of this pattern, or the next pattern: first object
+            if (k1 == P::RC - 1) {  // next pair of this pattern, or the next pattern
               const int np = last ? pat + (int)gridDim.x : pat;
-              patch_prefetch<P>(c, a.use_tma, &tm_a, 2 * np, np, npat, a.scan, g);
+              if (a.far_in)  // only second objects are gathered
+                patch_prefetch<P>(c, a.use_tma, &tm_b, 2 * np + 1, np, npat, a.scan, g);
+              else
+                patch_prefetch<P>(c, a.use_tma, &tm_a, 2 * np, np, npat, a.scan, g);
             }
           });
     }

@@ -841,53 +841,4 @@ __global__ void __launch_bounds__(P::NT) k_register(const PassArgs a,
   }
 }
 
-// ------------------------------------------------------------------------------------------
-// the family's dispatch table
-// ------------------------------------------------------------------------------------------
-template <class P>
-static void fill_tw_host(float2* tw) {
-  fill_twiddles<P>(tw);
-}
-
-template <class P>
-const PlanOps* make_ops() {
-  static PlanOps ops;
-  static bool init = false;
-  if (!init) {
-    ops.L = P::L;
-    ops.N = P::N;
-    ops.NT = P::NT;
-    ops.RC = P::RC;
-    ops.smem_bytes = Smem<P>::BYTES;
-    ops.smem_bytes_nodata = Smem<P>::BYTES_NODATA;
-    ops.smem_bytes_reg = RegGeom<P>::SMEM;
-    ops.scratch_per_cta = Scratch<P>::TOTAL;
-    ops.tw_total = TwLayout<P>::TOTAL;
-    ops.fill_tw = fill_tw_host<P>;
-    ops.patch_w = Patch<P>::TMA ? Patch<P>::W : 0;
-    ops.patch_h = Patch<P>::TMA ? Patch<P>::H : 0;
-#define PTX_SET(id, ...)                                   \
-  ops.kernels[id] = (const void*)(void (*)(const PassArgs, const CUtensorMap, const CUtensorMap))(__VA_ARGS__); \
-  ops.names[id] = #__VA_ARGS__;
-    PTX_SET(K_FWD, k_fwd<P>)
-    PTX_SET(K_NEAR, k_nearplane<P>)
-    PTX_SET(K_ADJ_OBJ, k_adj<P, 0>)
-    PTX_SET(K_ADJ_PRB, k_adj<P, 1>)
-    PTX_SET(K_INT_GAUSS, k_intensity<P, 0>)
-    PTX_SET(K_INT_POIS, k_intensity<P, 1>)
-    PTX_SET(K_GRAD_GAUSS_OBJ, k_grad<P, 0, 0>)
-    PTX_SET(K_GRAD_GAUSS_PRB, k_grad<P, 0, 1>)
-    PTX_SET(K_GRAD_POIS_OBJ, k_grad<P, 1, 0>)
-    PTX_SET(K_GRAD_POIS_PRB, k_grad<P, 1, 1>)
-    PTX_SET(K_LS_GAUSS, k_linesearch<P, 0>)
-    PTX_SET(K_LS_POIS, k_linesearch<P, 1>)
-    PTX_SET(K_REG_OBJ, k_register<P, 0>)
-    PTX_SET(K_REG_FOURIER, k_register<P, 1>)
-    PTX_SET(K_REG_REAL, k_register<P, 2>)
-#undef PTX_SET
-    init = true;
-  }
-  return &ops;
-}
-
 }  // namespace ptx

@@ -303,6 +303,9 @@ class CGPtychoSolver(PtychoCuFFT):
     position_upsample = 100
     #: step candidates evaluated per fused line-search pass
     ls_candidates = 4
+    #: keep F(psi, probe_k) of each gradient pass in HBM (8 N^2 B per pattern and mode) so that the
+    #: line search that follows does not gather and transform it again
+    cache_far_field = True
     #: diagnostics hook used by the parity tests: a list of raw line-search results, consumed in call
     #: order, that override the solver's own decisions (the costs are still evaluated and logged)
     _forced_steps = None
@@ -344,17 +347,20 @@ class CGPtychoSolver(PtychoCuFFT):
         return self._sum(red)
 
     def _grad(self, what, psi, scan, probe, mode, data, inten, fscale, iscale, gscale, model, out,
-              out_stride=0, sc=None):
-        """`sc`: device tensor {fscale, iscale, gscale} (then the three host values are ignored)."""
+              out_stride=0, sc=None, far_out=None):
+        """`sc`: device tensor {fscale, iscale, gscale} (then the three host values are ignored).
+        `far_out`: [T,S,N,N] complex64 that receives F(psi, probe[:, mode]) for the next line search."""
         if sc is None:
             sc = self._scalars(fscale, iscale, gscale)
         check(lib.ptx_cg_grad(self._h, what, _ptr(psi), _ptr(scan), _ptr(probe), probe.shape[1],
                               mode, _ptr(data), _ptr(inten) if inten is not None else None,
-                              _ptr(sc), model, _ptr(out), out_stride, current_stream()))
+                              _ptr(sc), model, _ptr(out), out_stride,
+                              _ptr(far_out) if far_out is not None else None, current_stream()))
 
     def _line_search(self, obj_a, prb_a, nm_a, m_a, obj_b, prb_b, nm_b, m_b, npairs, scan, data,
-                     p1, model):
-        """Fused line_search_sqr: evaluates `ls_candidates` halvings per pass (ptycho.py:272-281)."""
+                     p1, model, far_a=None):
+        """Fused line_search_sqr: evaluates `ls_candidates` halvings per pass (ptycho.py:272-281).
+        `far_a`: [npairs, T,S,N,N] cached first far fields (see `_grad(far_out=...)`)."""
         K = int(self.ls_candidates)
         c0 = 0
         forced = self._forced_steps.pop(0) if self._forced_steps else None
@@ -362,7 +368,8 @@ class CGPtychoSolver(PtychoCuFFT):
             cost = torch.zeros(9, dtype=torch.float64, device=obj_a.device)  # kernel reduces 1 + 8 slots
             check(lib.ptx_cg_linesearch(self._h, _ptr(obj_a), _ptr(prb_a), nm_a, m_a, _ptr(obj_b),
                                         _ptr(prb_b), nm_b, m_b, npairs, _ptr(scan), _ptr(data),
-                                        _ptr(p1) if p1 is not None else None, model, c0, K,
+                                        _ptr(p1) if p1 is not None else None,
+                                        _ptr(far_a) if far_a is not None else None, model, c0, K,
                                         _ptr(cost), current_stream()))
             c = self._sum(cost).cpu().numpy()
             self.ls_log.append((c0, c[:1 + K].copy()))
@@ -503,6 +510,9 @@ class CGPtychoSolver(PtychoCuFFT):
         dev = psi.device
         multi = M > 1
         inten = torch.empty_like(data) if multi else None
+        # F(psi, probe_k) of the gradient passes, re-read by the line searches that follow them
+        far = (torch.empty((M,) + tuple(data.shape), dtype=torch.complex64, device=dev)
+               if self.cache_far_field else None)
         sum_data = float(self._sum(data.sum(dtype=torch.float64).reshape(1))) if mdl == 0 else 0.0
 
         gradpsi = torch.zeros_like(psi)
@@ -541,12 +551,13 @@ class CGPtychoSolver(PtychoCuFFT):
             for k in range(M):
                 check(lib.ptx_cg_prep_gscale(_ptr(self._absmax(probe[:, k])), 1.0, _ptr(sc_obj),
                                              current_stream()))
-                self._grad(0, psi, scan, probe, k, data, inten, 0, 0, 0, mdl, gradpsi, sc=sc_obj)
+                self._grad(0, psi, scan, probe, k, data, inten, 0, 0, 0, mdl, gradpsi, sc=sc_obj,
+                           far_out=far[k] if far is not None else None)
             # Dai-Yuan direction (ptycho.py:364-372)
             self._dai_yuan(gradpsi, gradpsi0, dpsi, i == 0)
             # line search (ptycho.py:374-393)
             gammapsi = 0.5 * self._line_search(psi, probe, M, 0, dpsi, probe, M, 0, M, scan, data,
-                                               None, mdl)
+                                               None, mdl, far_a=far)
             if self.position_correction and i > 0:
                 # position correction (ptycho.py:398-403): register the all-ones-probe far fields of
                 # psi and psi + gamma dpsi for angle 0 and move its scan positions -- the caller's
@@ -577,14 +588,15 @@ class CGPtychoSolver(PtychoCuFFT):
                                                  current_stream()))
                     gradprb[m].zero_()
                     self._grad(1, psi, scan, probe, m, data, inten, 0, 0, 0, mdl, gradprb[m], P * P,
-                               sc=sc_prb)
+                               sc=sc_prb, far_out=far[m] if far is not None else None)
                     if self.comm is not None:
                         self.comm.probe_grad_(gradprb[m])
                     # Dai-Yuan direction (ptycho.py:442-450)
                     self._dai_yuan(gradprb[m], gradprb0[m], dprb[m], i == 0)
                     # line search (ptycho.py:451-461)
                     gammaprb = 0.5 * self._line_search(psi, probe, M, m, psi, dprb[m], 1, 0, 1,
-                                                       scan, data, inten, mdl)
+                                                       scan, data, inten, mdl,
+                                                       far_a=far[m] if far is not None else None)
                     # update probe (ptycho.py:463)
                     if T == 1:
                         self._axpy(probe[0, m], dprb[m, 0], gammaprb)
