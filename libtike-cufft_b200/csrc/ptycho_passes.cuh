@@ -486,6 +486,14 @@ __global__ void __launch_bounds__(P::NT) k_linesearch(const PassArgs a,
             });
       spectrum_pass<P>(
           c, p.skip, [&](int cb, float2(&v)[P::E]) {
+            if (t1c && cb == 0 && !p.skip && (c.tid & 15) == 0) {
+              // pull the cached far field from HBM into L2 meanwhile: a warp's register e covers two
+              // 128-byte lines (32 lanes x 8 B), one prefetch per line
+              for (int k1 = 0; k1 < P::RC; ++k1)
+#pragma unroll
+                for (int e = 0; e < P::E; ++e)
+                  asm volatile("prefetch.global.L2 [%0];" ::"l"(t1c + spec_index<P>(c, k1, e)));
+            }
             gather_any<P>(v, c, cb, a.use_tma, &tm_b, 2 * pat + 1, t, psi_b, prb_b, g, p);
           },
           [&](int k1, float2(&v)[P::E]) {
@@ -496,43 +504,55 @@ __global__ void __launch_bounds__(P::NT) k_linesearch(const PassArgs a,
             for (int q = 0; q < 5; ++q) cost[q] = 0.f;
             const float2* t1p = (t1c && !p.skip) ? t1c + c.sbase + k1 * P::N : nullptr;
             if (last) dp_wait<P>(c);
+            // the first far field comes from L2 / HBM: its loads are issued CH at a time ahead of
+            // the arithmetic that consumes them (one exposed round trip per CH pixels, not per pixel)
+            constexpr int CH = 8;
 #pragma unroll
-            for (int e = 0; e < P::E; ++e) {
-              float2 t1;
-              if (t1c) {  // block-uniform
-                int dx, dy;
-                elem_offset<typename P::S2>(e, dx, dy);
-                t1 = t1p ? __ldcg(t1p + (P::RC * pos_to_freq_y<P>(dy) * P::N + pos_to_freq_x<P>(dx)))
-                         : make_float2(0.f, 0.f);
-              } else {
-                t1 = st[e * P::NT];
-              }
-              const float2 t2 = v[e];
-              float q1 = t1.x * t1.x + t1.y * t1.y;
-              float q2 = t2.x * t2.x + t2.y * t2.y;
-              float q3 = 2.f * (t1.x * t2.x + t1.y * t2.y);
-              if (multi) {
-                if (!first) {
-                  q1 += ap[e * P::NT];
-                  q2 += ap[NN + e * P::NT];
-                  q3 += ap[2 * NN + e * P::NT];
-                }
-                if (!last) {
-                  ap[e * P::NT] = q1;
-                  ap[NN + e * P::NT] = q2;
-                  ap[2 * NN + e * P::NT] = q3;
+            for (int e0 = 0; e0 < P::E; e0 += CH) {
+              float2 t1v[CH];
+#pragma unroll
+              for (int j = 0; j < CH; ++j) {
+                const int e = e0 + j;
+                if (t1c) {  // block-uniform
+                  int dx, dy;
+                  elem_offset<typename P::S2>(e, dx, dy);
+                  t1v[j] = t1p ? __ldcg(t1p + (P::RC * pos_to_freq_y<P>(dy) * P::N + pos_to_freq_x<P>(dx)))
+                               : make_float2(0.f, 0.f);
+                } else {
+                  t1v[j] = st[e * P::NT];
                 }
               }
-              if (last) {
-                const float dd = c.dbuf[data_index<P>(c, e)];
-                const float sqd = fsqrt(dd);
-                if (p1in) q1 = __ldg(p1in + spec_index<P>(c, k1, e));
-                cost[0] += minf_px<MODEL>(q1, dd, sqd);
-                float gam = gam0;
 #pragma unroll
-                for (int q = 0; q < 4; ++q) {
-                  cost[1 + q] += minf_px<MODEL>(q1 + gam * gam * q2 + gam * q3, dd, sqd);
-                  gam *= 0.5f;
+              for (int j = 0; j < CH; ++j) {
+                const int e = e0 + j;
+                const float2 t1 = t1v[j];
+                const float2 t2 = v[e];
+                float q1 = t1.x * t1.x + t1.y * t1.y;
+                float q2 = t2.x * t2.x + t2.y * t2.y;
+                float q3 = 2.f * (t1.x * t2.x + t1.y * t2.y);
+                if (multi) {
+                  if (!first) {
+                    q1 += ap[e * P::NT];
+                    q2 += ap[NN + e * P::NT];
+                    q3 += ap[2 * NN + e * P::NT];
+                  }
+                  if (!last) {
+                    ap[e * P::NT] = q1;
+                    ap[NN + e * P::NT] = q2;
+                    ap[2 * NN + e * P::NT] = q3;
+                  }
+                }
+                if (last) {
+                  const float dd = c.dbuf[data_index<P>(c, e)];
+                  const float sqd = fsqrt(dd);
+                  if (p1in) q1 = __ldg(p1in + spec_index<P>(c, k1, e));
+                  cost[0] += minf_px<MODEL>(q1, dd, sqd);
+                  float gam = gam0;
+#pragma unroll
+                  for (int q = 0; q < 4; ++q) {
+                    cost[1 + q] += minf_px<MODEL>(q1 + gam * gam * q2 + gam * q3, dd, sqd);
+                    gam *= 0.5f;
+                  }
                 }
               }
             }
