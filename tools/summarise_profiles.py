@@ -54,16 +54,20 @@ if os.path.exists(os.path.join(g, "launches_bench.csv")):
     launches(os.path.join(g, "launches_bench.csv"), os.path.join(p, tag + "_bench_launch_shares.txt"))
 for rep, note in (("all128", "every fused pass at 128^2 (tools/prof.py 128 4: 4 angles x 1024 positions)"),
                   ("all256", "fused passes at 256^2 (tools/prof.py 256 1)"),
-                  ("bench_grad", "k_grad inside bench.py (c2, 8 angles x 1024 positions): the roofline.traffic source")):
+                  ("bench_grad", "k_grad inside bench.py (c2, 8 angles x 1024 positions): the roofline.traffic source"),
+                  ("bench_grad_c4", "k_grad inside bench.py --workload c4 (2 angles x 1024 positions, 256^2): the roofline.traffic source")):
     path = os.path.join(g, rep + "_raw.csv")
     if os.path.exists(path):
         hdr, units, body = summarise(path, os.path.join(p, "%s_%s_ncu.txt" % (tag, rep)), note)
-        if rep == "bench_grad" and body:
+        if rep in ("bench_grad", "bench_grad_c4") and body:
             ix = {h: i for i, h in enumerate(hdr)}
             def mb(k):
                 v = float(body[0][ix[k]]); u = units[ix[k]]
                 return v * {"Gbyte": 1e9, "Mbyte": 1e6, "Kbyte": 1e3, "byte": 1}[u]
             t = mb("dram__bytes_read.sum") + mb("dram__bytes_write.sum")
-            json.dump({"c2": t}, open(os.path.join(p, "traffic.json"), "w"))
-            print("traffic c2 bytes/launch:", t)
+            tj = os.path.join(p, "traffic.json")
+            cur = json.load(open(tj)) if os.path.exists(tj) else {}
+            cur["c2" if rep == "bench_grad" else "c4"] = t
+            json.dump(cur, open(tj, "w"))
+            print("traffic", rep, "bytes/launch:", t)
 print("done")
