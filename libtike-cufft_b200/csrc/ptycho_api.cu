@@ -178,11 +178,10 @@ struct ptx_plan {
   float2* scratch;
   size_t scratch_per_cta;  // float2
   Geo geo;
-  // position correction (lazy): E table of the last upsampling factor, all-ones probe
+  // position correction (lazy): tables of the last upsampling factor
   double2* reg_E;
   double* reg_AT;  // [REG_NQ][N] Bessel table followed by [REG_JROWS][REG_NQ] Chebyshev table
   int reg_uf;
-  float2* ones;
 };
 
 static const PlanOps* ops_for(int L) {
@@ -362,7 +361,6 @@ int ptx_create(ptx_plan** out, size_t ptheta, size_t nz, size_t n, size_t nscan,
   p->reg_E = nullptr;
   p->reg_AT = nullptr;
   p->reg_uf = 0;
-  p->ones = nullptr;
   p->geo.T = (int)ptheta; p->geo.nz = (int)nz; p->geo.n = (int)n; p->geo.S = (int)nscan;
   p->geo.P = (int)nprb; p->geo.N = (int)ndet; p->geo.o = (int)((ndet - nprb) / 2);
   p->geo.kappa = 1.0f / (float)ndet;
@@ -396,13 +394,11 @@ int ptx_free(ptx_plan* p) {
     cudaFree(p->scratch);
     if (p->reg_E) cudaFree(p->reg_E);
     if (p->reg_AT) cudaFree(p->reg_AT);
-    if (p->ones) cudaFree(p->ones);
     p->tw = nullptr;
     p->scratch = nullptr;
     p->reg_E = nullptr;
     p->reg_AT = nullptr;
-    p->ones = nullptr;
-    p->freed = true;
+      p->freed = true;
   }
   return PTX_OK;
 }
@@ -690,18 +686,11 @@ int ptx_cg_position_shifts(ptx_plan* p, const void* psi_a, const void* psi_b, co
   int U = 0;
   rc = reg_prepare(p, upsample_factor, &U, st);
   if (rc) return rc;
-  if (!p->ones) {
-    const size_t pp = p->nprb * p->nprb;
-    std::vector<float2> h(pp, make_float2(1.f, 0.f));
-    CUDA_TRY(cudaMalloc(&p->ones, pp * sizeof(float2)));
-    CUDA_TRY(cudaMemcpy(p->ones, h.data(), pp * sizeof(float2), cudaMemcpyHostToDevice));
-  }
   PassArgs a = base_args(p);
   a.g.T = 1;  // angle 0 of the chunk only, like the reference (ptycho.py:399-403)
   a.psi = (const float2*)psi_a;
   a.psi_b = (const float2*)psi_b;
   a.scan = (const float2*)scan;
-  a.prb = p->ones;
   a.reg_E = p->reg_E;
   a.reg_U = U;
   a.reg_uf = upsample_factor;

@@ -725,6 +725,34 @@ __device__ __forceinline__ int register_refine_cheb(const float2* __restrict__ p
   return block_argmax<NW>(best, red, tid);
 }
 
+// near plane under an all-ones probe (ptycho.py:399-400: probe[:, 0] * 0 + 1): kappa * patch inside
+// the probe window, no probe loads
+template <class P, bool INSIDE>
+__device__ __forceinline__ void gather_ones_impl(float2 (&v)[P::E], const Cta<P>& c, int cb,
+                                                 const float2* __restrict__ psi_t, const Geo& g,
+                                                 const Pat& p) {
+#pragma unroll
+  for (int e = 0; e < P::E; ++e) {
+    int y, x;
+    nat_coord<P>(c, cb, e, y, x);
+    const int iy = y - g.o, ix = x - g.o;
+    float2 r = make_float2(0.f, 0.f);
+    if ((unsigned)iy < (unsigned)g.P && (unsigned)ix < (unsigned)g.P) {
+      const float2 t = patch_at<INSIDE>(psi_t, g, p, iy, ix);
+      r = make_float2(g.kappa * t.x, g.kappa * t.y);
+    }
+    v[e] = r;
+  }
+}
+template <class P>
+__device__ __forceinline__ void gather_ones(float2 (&v)[P::E], const Cta<P>& c, int cb,
+                                            const float2* __restrict__ psi_t, const Geo& g, const Pat& p) {
+  if (p.inside)
+    gather_ones_impl<P, true>(v, c, cb, psi_t, g, p);
+  else
+    gather_ones_impl<P, false>(v, c, cb, psi_t, g, p);
+}
+
 // MODE 0: far fields of two OBJECTS under an all-ones probe at the scan positions (ptycho.py:398-401)
 // MODE 1: src / target given in Fourier space [S,N,N] (register_translation_batch(space='fourier'))
 // MODE 2: src / target given in real space [S,N,N]    (space='real': fft2 of both first)
@@ -763,10 +791,18 @@ __global__ void __launch_bounds__(P::NT) k_register(const PassArgs a,
     bst.i = 0;
     // v holds the target's spectrum; src_at(e) fetches the source's
     auto product = [&](int k1, float2(&v)[P::E], auto src_at) {
+      constexpr int CH = 8;  // source loads in flight ahead of their use (one round trip per CH pixels)
 #pragma unroll
-      for (int e = 0; e < P::E; ++e) {
-        v[e] = cmulc(src_at(e), v[e]);  // src * conj(target), complex64 (ptycho.py:207)
-        __stcg(praw + spec_index<P>(c, k1, e), v[e]);
+      for (int e0 = 0; e0 < P::E; e0 += CH) {
+        float2 sv[CH];
+#pragma unroll
+        for (int j = 0; j < CH; ++j) sv[j] = src_at(e0 + j);
+#pragma unroll
+        for (int j = 0; j < CH; ++j) {
+          const int e = e0 + j;
+          v[e] = cmulc(sv[j], v[e]);  // src * conj(target), complex64 (ptycho.py:207)
+          __stcg(praw + spec_index<P>(c, k1, e), v[e]);
+        }
       }
     };
     auto peak = [&](int cb, float2(&v)[P::E]) {
@@ -787,9 +823,9 @@ __global__ void __launch_bounds__(P::NT) k_register(const PassArgs a,
           },
           peak);
     } else {
-      auto load_nat = [&](const float2* img, const float2* ones, int cb, float2(&v)[P::E]) {
+      auto load_nat = [&](const float2* img, int cb, float2(&v)[P::E]) {
         if (MODE == 0) {
-          gather_nat<P>(v, c, cb, img, ones, g, p);
+          gather_ones<P>(v, c, cb, img, g, p);
         } else {
 #pragma unroll
           for (int e = 0; e < P::E; ++e) {
@@ -800,7 +836,7 @@ __global__ void __launch_bounds__(P::NT) k_register(const PassArgs a,
         }
       };
       spectrum_pass<P>(
-          c, false, [&](int cb, float2(&v)[P::E]) { load_nat(src, a.prb, cb, v); },
+          c, false, [&](int cb, float2(&v)[P::E]) { load_nat(src, cb, v); },
           [&](int k1, float2(&v)[P::E]) {
             float2* st = c.stash + (size_t)k1 * P::E * P::NT + c.tid;
 #pragma unroll
@@ -808,7 +844,7 @@ __global__ void __launch_bounds__(P::NT) k_register(const PassArgs a,
           },
           [&](int) {});
       fused_pass<P>(
-          c, [&](int cb, float2(&v)[P::E]) { load_nat(tgt, a.prb, cb, v); },
+          c, [&](int cb, float2(&v)[P::E]) { load_nat(tgt, cb, v); },
           [&](int k1, float2(&v)[P::E]) {
             const float2* st = c.stash + (size_t)k1 * P::E * P::NT + c.tid;
             product(k1, v, [&](int e) { return st[e * P::NT]; });
