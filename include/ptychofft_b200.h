@@ -122,13 +122,16 @@ int ptx_cg_grad(ptx_plan* p, int what, const void* psi, const void* scan, const 
  *   p1 += |t1|^2 ; p2 += |t2|^2 ; p3 += 2 Re(t1 conj t2)      (p1 = p1_in when given)
  *   cost[0] += minf(p1) ; cost[1+c] += minf(p1 + g^2 p2 + g p3), g = 2^-(c0+c), c < 4
  * Pair j uses modes (mode_a0 + j, mode_b0 + j).  The kernel always evaluates four candidates per
- * pass (ncand <= 4 tells how many the caller will look at).  cost: 9 doubles, caller-zeroed.
+ * pass (ncand <= 4 tells how many the caller will look at).  cost: 16 doubles, caller-zeroed.
  * far_a (nullable): [npairs][T,S,N,N] c64 -- t1 of every pair as left by ptx_cg_grad(far_out); when
- * given, obj_a / prb_a are not transformed again (skipped positions read as 0). */
+ * given, obj_a / prb_a are not transformed again (skipped positions read as 0).
+ * want_ab != 0: additionally cost[5+c] += sum sqrt(I_c data) and cost[10+c] += sum I_c for the five
+ * intensities I_c evaluated (c = 0: p1), i.e. the a and b of ptycho.py:342-343 that the NEXT
+ * iteration would compute from the accepted candidate; cost then is 16 doubles. */
 int ptx_cg_linesearch(ptx_plan* p, const void* obj_a, const void* prb_a, int nmodes_a, int mode_a0,
                       const void* obj_b, const void* prb_b, int nmodes_b, int mode_b0, int npairs,
                       const void* scan, const float* data, const float* p1_in, const void* far_a,
-                      int model, int c0, int ncand, double* cost, void* stream);
+                      int model, int c0, int ncand, int want_ab, double* cost, void* stream);
 
 /* ---------------------------------------------------------------------------------------
  * Position correction (ptycho.py:163-248, called from the CG loop at ptycho.py:398-403).

@@ -272,7 +272,7 @@ static int launch(ptx_plan* p, int kid, PassArgs& a, cudaStream_t st) {
     const char* e = getenv("PTX_TMA_GATHER");
     return !e ? 1 : !strcmp(e, "off") ? 0 : !strcmp(e, "all") ? 2 : 1;
   }();
-  const bool ls = (kid == K_LS_GAUSS || kid == K_LS_POIS);
+  const bool ls = (kid == K_LS_GAUSS || kid == K_LS_POIS || kid == K_LSAB_GAUSS || kid == K_LSAB_POIS);
   const bool inten = (kid == K_INT_GAUSS || kid == K_INT_POIS);
   // the object-gradient pass of the 64^2 plan gathers the NEXT pattern inside its scatter loop
   // (scatter_gather_impl) with plain loads: no tensor map under any policy
@@ -281,7 +281,7 @@ static int launch(ptx_plan* p, int kid, PassArgs& a, cudaStream_t st) {
   const bool want = !grad_obj1 &&
                     (policy == 2 || (policy == 1 && (ls || inten || (ops->RC > 1 && kid == K_FWD))));
   if (want && kid != K_NEAR && kid != K_ADJ_OBJ && kid != K_ADJ_PRB && !reg_kernel(kid) && a.psi) {
-    const bool two = (kid == K_LS_GAUSS || kid == K_LS_POIS);
+    const bool two = ls;
     if (make_object_map(p, a.psi, &tm_a) && (!two || make_object_map(p, a.psi_b, &tm_b))) a.use_tma = 1;
   }
   void* params[] = {&a, &tm_a, &tm_b};
@@ -530,7 +530,7 @@ int ptx_cg_grad(ptx_plan* p, int what, const void* psi, const void* scan, const 
 int ptx_cg_linesearch(ptx_plan* p, const void* obj_a, const void* prb_a, int nmodes_a, int mode_a0,
                       const void* obj_b, const void* prb_b, int nmodes_b, int mode_b0, int npairs,
                       const void* scan, const float* data, const float* p1_in, const void* far_a,
-                      int model, int c0, int ncand, double* cost, void* stream) {
+                      int model, int c0, int ncand, int want_ab, double* cost, void* stream) {
   int rc = check_plan(p);
   if (rc) return rc;
   if (!obj_a || !prb_a || !obj_b || !prb_b || !scan || !data || !cost || npairs < 1 || ncand < 1 ||
@@ -557,8 +557,8 @@ int ptx_cg_linesearch(ptx_plan* p, const void* obj_a, const void* prb_a, int nmo
   a.ncand = ncand;
   a.red = cost;
   cudaStream_t st = (cudaStream_t)stream;
-  if (model == PTX_MODEL_GAUSSIAN) return launch(p, K_LS_GAUSS, a, st);
-  if (model == PTX_MODEL_POISSON) return launch(p, K_LS_POIS, a, st);
+  if (model == PTX_MODEL_GAUSSIAN) return launch(p, want_ab ? K_LSAB_GAUSS : K_LS_GAUSS, a, st);
+  if (model == PTX_MODEL_POISSON) return launch(p, want_ab ? K_LSAB_POIS : K_LS_POIS, a, st);
   return fail(PTX_EINVAL, "unknown model %d", model);
 }
 

@@ -55,6 +55,7 @@ enum KernelId {
   K_GRAD_GAUSS_OBJ, K_GRAD_GAUSS_PRB, K_GRAD_POIS_OBJ, K_GRAD_POIS_PRB, K_LS_GAUSS, K_LS_POIS,
   K_REG_OBJ, K_REG_FOURIER, K_REG_REAL,
   K_GRADC_GAUSS_OBJ, K_GRADC_GAUSS_PRB, K_GRADC_POIS_OBJ, K_GRADC_POIS_PRB,  // + far-field cache output
+  K_LSAB_GAUSS, K_LSAB_POIS,  // + the next iteration's a, b sums of every candidate
   K_COUNT
 };
 

@@ -17,7 +17,7 @@ struct Smem {
                                   ? ((Patch<P>::WORDS + 15) / 16 * 16)
                                   : TileGeom<P>::WORDS;
   static constexpr int TW = TwLayout<P>::TOTAL;    // float2
-  static constexpr int RED = (P::NT / 32) * 12;    // doubles: cross-warp reduction scratch
+  static constexpr int RED = (P::NT / 32) * 16;    // doubles: cross-warp reduction scratch
   static constexpr int DBUF = P::NX * P::NY;       // floats: measured-data tile (TMA bulk copy)
   static constexpr size_t OFF_TW = (size_t)TILE * sizeof(float2);
   // [tile | twiddles | reduction scratch | mbarrier | data tile]: kernels that never read measured
@@ -34,7 +34,7 @@ struct Scratch {  // per-CTA global scratch, in float2
   static constexpr size_t FRAME = P::RC > 1 ? (size_t)P::N * P::N : 0;
   static constexpr size_t STASH = (size_t)P::N * P::N;
   static constexpr size_t ACCP = (size_t)3 * P::N * P::N / 2;
-  static constexpr size_t SLOTS = (size_t)9 * P::NT;  // doubles = float2-sized
+  static constexpr size_t SLOTS = (size_t)16 * P::NT;  // doubles = float2-sized
   static constexpr size_t TOTAL = FRAME + STASH + ACCP + SLOTS;
 };
 
@@ -54,7 +54,7 @@ __device__ __forceinline__ void cta_setup(Cta<P>& c, unsigned char* raw, const P
   c.accp = reinterpret_cast<float*>(c.stash + Scratch<P>::STASH);
   c.slots = reinterpret_cast<double*>(c.stash + Scratch<P>::STASH + Scratch<P>::ACCP) + c.tid;
 #pragma unroll
-  for (int k = 0; k < 9; ++k) c.slots[k * P::NT] = 0.0;
+  for (int k = 0; k < 16; ++k) c.slots[k * P::NT] = 0.0;
   fixed_coords<typename P::S0, P::WBITS>(c.tid, c.xf0, c.yf0);
   fixed_coords<typename P::S2, P::WBITS>(c.tid, c.xf2, c.yf2);
   c.sbase = spec_base<P>(c.xf2, c.yf2);
@@ -258,6 +258,23 @@ __global__ void __launch_bounds__(P::NT) k_adj(const PassArgs a, const __grid_co
   if (FLG == 1 && t_cur >= 0) pacc_flush<P>(c, a.grad + (size_t)t_cur * a.grad_ts, g);
 }
 
+// minf_px plus the two sums of the NEXT iteration's intensity pass for the same intensity x
+// (ptycho.py:342-343: a = sum sqrt(I d), b = sum I): the probe line search evaluates exactly the
+// intensity the next iteration starts from, so that pass need not run again (M = 1).
+template <int MODEL>
+__device__ __forceinline__ float minf_ab_px(float x, float d, float sqd, float& sa, float& sb) {
+  const float ax = fabsf(x);
+  const float sx = fsqrt(ax);
+  sa += sx * sqd;
+  sb += x;
+  if (MODEL == PTX_MODEL_GAUSSIAN) {
+    const float r = sx - sqd;
+    return r * r;
+  } else {
+    return ax - d * logf(ax + 1e-32f);
+  }
+}
+
 // ------------------------------------------------------------------------------------------
 // CG pass A: I = sum_k |F_k|^2, reductions a = sum sqrt(I d), b = sum I, cost   (ptycho.py:330-343)
 // With several modes the running sum is parked in thread-private scratch between modes.
@@ -445,7 +462,7 @@ __global__ void __launch_bounds__(P::NT) k_grad(const PassArgs a, const __grid_c
 //   ptycho.py:383-393 (object), 451-461 (probe), 253-281 (line_search_sqr)
 // The first far field of a pair is parked in thread-private scratch while the second is transformed.
 // ------------------------------------------------------------------------------------------
-template <class P, int MODEL>
+template <class P, int MODEL, bool AB>
 __global__ void __launch_bounds__(P::NT) k_linesearch(const PassArgs a,
                                                       const __grid_constant__ CUtensorMap tm_a,
                                                       const __grid_constant__ CUtensorMap tm_b) {
@@ -500,8 +517,11 @@ __global__ void __launch_bounds__(P::NT) k_linesearch(const PassArgs a,
             const float2* st = c.stash + (size_t)k1 * P::E * P::NT + c.tid;
             float* ap = c.accp + (size_t)k1 * P::E * P::NT + c.tid;
             float cost[5];  // fp32 over 32 pixels, double across tiles
+            float sab[AB ? 10 : 1];  // a and b of every candidate (AB)
 #pragma unroll
             for (int q = 0; q < 5; ++q) cost[q] = 0.f;
+#pragma unroll
+            for (int q = 0; q < (AB ? 10 : 1); ++q) sab[q] = 0.f;
             const float2* t1p = (t1c && !p.skip) ? t1c + c.sbase + k1 * P::N : nullptr;
             if (last) dp_wait<P>(c);
             // the first far field comes from L2 / HBM: its loads are issued CH at a time ahead of
@@ -546,12 +566,22 @@ __global__ void __launch_bounds__(P::NT) k_linesearch(const PassArgs a,
                   const float dd = c.dbuf[data_index<P>(c, e)];
                   const float sqd = fsqrt(dd);
                   if (p1in) q1 = __ldg(p1in + spec_index<P>(c, k1, e));
-                  cost[0] += minf_px<MODEL>(q1, dd, sqd);
                   float gam = gam0;
+                  if (AB) {
+                    cost[0] += minf_ab_px<MODEL>(q1, dd, sqd, sab[0], sab[5]);
 #pragma unroll
-                  for (int q = 0; q < 4; ++q) {
-                    cost[1 + q] += minf_px<MODEL>(q1 + gam * gam * q2 + gam * q3, dd, sqd);
-                    gam *= 0.5f;
+                    for (int q = 0; q < 4; ++q) {
+                      cost[1 + q] += minf_ab_px<MODEL>(q1 + gam * gam * q2 + gam * q3, dd, sqd, sab[1 + q],
+                                                       sab[6 + q]);
+                      gam *= 0.5f;
+                    }
+                  } else {
+                    cost[0] += minf_px<MODEL>(q1, dd, sqd);
+#pragma unroll
+                    for (int q = 0; q < 4; ++q) {
+                      cost[1 + q] += minf_px<MODEL>(q1 + gam * gam * q2 + gam * q3, dd, sqd);
+                      gam *= 0.5f;
+                    }
                   }
                 }
               }
@@ -559,6 +589,10 @@ __global__ void __launch_bounds__(P::NT) k_linesearch(const PassArgs a,
             if (last) {
 #pragma unroll
               for (int q = 0; q < 5; ++q) c.slots[q * P::NT] += (double)cost[q];
+              if (AB) {
+#pragma unroll
+                for (int q = 0; q < 10; ++q) c.slots[(5 + q) * P::NT] += (double)sab[q];
+              }
             }
           },
           [&](int k1) {
@@ -573,10 +607,10 @@ __global__ void __launch_bounds__(P::NT) k_linesearch(const PassArgs a,
           });
     }
   }
-  double acc[5];
+  double acc[AB ? 15 : 5];
 #pragma unroll
-  for (int q = 0; q < 5; ++q) acc[q] = c.slots[q * P::NT];
-  block_reduce_add<5, P::NT / 32>(acc, c.red, a.red, c.tid);
+  for (int q = 0; q < (AB ? 15 : 5); ++q) acc[q] = c.slots[q * P::NT];
+  block_reduce_add<(AB ? 15 : 5), P::NT / 32>(acc, c.red, a.red, c.tid);
 }
 
 }  // namespace ptx

@@ -306,6 +306,10 @@ class CGPtychoSolver(PtychoCuFFT):
     #: keep F(psi, probe_k) of each gradient pass in HBM (8 N^2 B per pattern and mode) so that the
     #: line search that follows does not gather and transform it again
     cache_far_field = True
+    #: single-mode runs with probe recovery: take the a, b sums (and cost) that open the next
+    #: iteration (ptycho.py:330-343) from the probe line search, which has just evaluated exactly
+    #: that intensity, instead of running the intensity pass again
+    reuse_line_search_sums = True
     #: diagnostics hook used by the parity tests: a list of raw line-search results, consumed in call
     #: order, that override the solver's own decisions (the costs are still evaluated and logged)
     _forced_steps = None
@@ -358,30 +362,43 @@ class CGPtychoSolver(PtychoCuFFT):
                               _ptr(far_out) if far_out is not None else None, current_stream()))
 
     def _line_search(self, obj_a, prb_a, nm_a, m_a, obj_b, prb_b, nm_b, m_b, npairs, scan, data,
-                     p1, model, far_a=None):
+                     p1, model, far_a=None, want_ab=False):
         """Fused line_search_sqr: evaluates `ls_candidates` halvings per pass (ptycho.py:272-281).
-        `far_a`: [npairs, T,S,N,N] cached first far fields (see `_grad(far_out=...)`)."""
+        `far_a`: [npairs, T,S,N,N] cached first far fields (see `_grad(far_out=...)`).
+        `want_ab`: also reduce a = sum sqrt(I data), b = sum I for every candidate intensity; after
+        the call `self._ls_ab` holds (a, b, cost) of the intensity at HALF the returned step -- the
+        update the solver applies (ptycho.py:393, 461) -- or None when that candidate was not among
+        the ones evaluated in the deciding pass."""
         K = int(self.ls_candidates)
         c0 = 0
         forced = self._forced_steps.pop(0) if self._forced_steps else None
+        self._ls_ab = None
+
+        def done(step, c):
+            if want_ab:
+                j = 0 if step == 0 else int(round(-np.log2(step))) - c0 + 2  # slot of step / 2
+                if 0 <= j <= 4:
+                    self._ls_ab = (c[5 + j], c[10 + j], c[j])
+            return step
+
         while True:
-            cost = torch.zeros(9, dtype=torch.float64, device=obj_a.device)  # kernel reduces 1 + 8 slots
+            cost = torch.zeros(16, dtype=torch.float64, device=obj_a.device)  # 5 costs (+ 5 a + 5 b)
             check(lib.ptx_cg_linesearch(self._h, _ptr(obj_a), _ptr(prb_a), nm_a, m_a, _ptr(obj_b),
                                         _ptr(prb_b), nm_b, m_b, npairs, _ptr(scan), _ptr(data),
                                         _ptr(p1) if p1 is not None else None,
                                         _ptr(far_a) if far_a is not None else None, model, c0, K,
-                                        _ptr(cost), current_stream()))
+                                        1 if want_ab else 0, _ptr(cost), current_stream()))
             c = self._sum(cost).cpu().numpy()
             self.ls_log.append((c0, c[:1 + K].copy()))
             if forced is not None and (forced == 0 or forced >= 2.0 ** -(c0 + K - 1)):
-                return forced
+                return done(forced, c)
             for j in range(K):
                 step = 2.0 ** -(c0 + j)
                 if forced is None and not (c[1 + j] > c[0]):
-                    return step
+                    return done(step, c)
                 if step < 1e-32:
                     warnings.warn("Line search failed for conjugate gradient.")
-                    return 0
+                    return done(0, c)
             c0 += K
 
     def _dai_yuan(self, grad, grad0, d, first):
@@ -530,13 +547,19 @@ class CGPtychoSolver(PtychoCuFFT):
         print("# congujate gradient parameters\n"
               "iteration, step size object, step size probe, function min")  # csv column headers
         gammaprb = 0
+        carried = None
+        reuse = bool(self.reuse_line_search_sums) and M == 1 and recover_prb
         self.history = []  # (iteration, step size object, step size probe) -- diagnostics only
         self.ls_log = []   # (first candidate exponent, [f(0), f(2^-c0), ...]) per fused pass
         self.shift_log = []  # device [S,2] float64 shifts of every position-correction step
         for i in range(piter):
             # 1) object retrieval subproblem with fixed probes (ptycho.py:327-345).  a, b, the probe
             # rescaling and the gradient scalars stay on the device: no host round trip here
-            red = self._intensity(psi, scan, probe, data, inten, mdl)
+            if carried is not None:  # a, b, cost of this very intensity, from the last line search
+                red = torch.tensor(carried, dtype=torch.float64, device=dev)
+                carried = None
+            else:
+                red = self._intensity(psi, scan, probe, data, inten, mdl)
             check(lib.ptx_cg_prep_scale(_ptr(red), mdl, _ptr(s_dev), _ptr(sc_obj), current_stream()))
             check(lib.ptx_vec_scale(_ptr(probe), probe.numel(), _ptr(s_dev), current_stream()))
             if i % 32 == 0:  # cost of this iteration's absfpsi, printed below (ptycho.py:481-482)
@@ -596,7 +619,10 @@ class CGPtychoSolver(PtychoCuFFT):
                     # line search (ptycho.py:451-461)
                     gammaprb = 0.5 * self._line_search(psi, probe, M, m, psi, dprb[m], 1, 0, 1,
                                                        scan, data, inten, mdl,
-                                                       far_a=far[m] if far is not None else None)
+                                                       far_a=far[m] if far is not None else None,
+                                                       want_ab=reuse)
+                    if reuse and self._ls_ab is not None:
+                        carried = [float(x) for x in self._ls_ab]
                     # update probe (ptycho.py:463)
                     if T == 1:
                         self._axpy(probe[0, m], dprb[m, 0], gammaprb)
