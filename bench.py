@@ -299,6 +299,8 @@ def run_b200(args, world, rank, local):
                         torch.cuda.synchronize()
                         dt = time.perf_counter() - t0
                     cg[key] = 16 / dt
+                    if on:  # it varies with the data: fused 4-candidate passes
+                        cg["line_search_passes_per_iter"] = len(s1.ls_log) / 16.0
     if world > 1:
         barrier(world)
     if rank != 0:

@@ -321,3 +321,30 @@ def test_cg_skipped_positions_window_and_two_angles(ndet, nprb, model, poscorr):
             for a, b in zip(glog, rlog):
                 assert np.array_equal(a[0], [-0.75, -0.75]) and np.array_equal(b[0], [-0.75, -0.75])
                 assert np.abs(a - b).max() <= 0.0100001
+
+
+@pytest.mark.parametrize("model,ndet", [("gaussian", 128), ("poisson", 64), ("gaussian", 256)])
+def test_cg_shortcuts_do_not_change_results(model, ndet):
+    """The two HBM shortcuts of the loop -- far field of the gradient pass re-read by the line search
+    (cache_far_field) and the next iteration's a, b taken from the probe line search
+    (reuse_line_search_sums) -- against the same solver with both switched off, position correction
+    on: identical step decisions, psi / probe within the operator bar."""
+    pt = _pt()
+    data, psi0, scan, prb0 = _problem(1, 49, model, ndet)
+    nscan = scan.shape[1]
+    nz, n = psi0.shape[1:]
+    res = {}
+    for fast in (False, True):
+        with pt.CGPtychoSolver(nscan, ndet, ndet, 1, nz, n) as slv:
+            slv.position_correction = True
+            slv.cache_far_field = fast
+            slv.reuse_line_search_sums = fast
+            res[fast] = (slv.run_batch(data, psi0, scan, prb0, piter=6, model=model, recover_prb=True),
+                         list(slv.history))
+    # steps below 1e-6 are searches that effectively failed (costs equal to fp32 resolution): how
+    # many halvings they take is noise and the update they apply is nil
+    sig = lambda hist: [tuple(x if x > 1e-6 else 0.0 for x in h[1:]) for h in hist]  # noqa: E731
+    assert sig(res[True][1]) == sig(res[False][1])
+    e = (rel_l2(res[True][0]["psi"], res[False][0]["psi"]), rel_l2(res[True][0]["probe"], res[False][0]["probe"]))
+    print("shortcuts on vs off: psi %.2e probe %.2e" % e)
+    assert max(e) < 1e-5

@@ -3,6 +3,7 @@
     ncu --set full --clock-control none --import-source on -k regex:k_grad -s 2 -c 1 \
         -o gpurun_out/grad128 python tools/prof.py 128 4
 """
+import ctypes
 import os
 import sys
 
@@ -39,6 +40,17 @@ def main(ndet=128, T=4, reps=3, nmodes=1):
             slv.ls_log = []
             slv._line_search(psi1, probe, nmodes, 0, dpsi, probe, nmodes, 0, nmodes, scan, data,
                              None, 0)
+            # cached / a-b variants of the CG loop and the position-correction kernel
+            far = torch.empty((nmodes,) + tuple(data.shape), dtype=torch.complex64, device="cuda")
+            slv._grad(0, psi1, scan, probe, 0, data, None, 1.0, 1.0, 1.0, 0, gradpsi, far_out=far[0])
+            slv._line_search(psi1, probe, nmodes, 0, dpsi, probe, nmodes, 0, nmodes, scan, data,
+                             None, 0, far_a=far, want_ab=True)
+            shifts = torch.empty((S, 2), dtype=torch.float64, device="cuda")
+            psi2 = (psi1 + 0.5 * dpsi).contiguous()
+            pt.ptycho.check(pt.ptycho.lib.ptx_cg_position_shifts(
+                slv._h, ctypes.c_void_p(psi1.data_ptr()), ctypes.c_void_p(psi2.data_ptr()),
+                ctypes.c_void_p(scan.data_ptr()), 100, ctypes.c_void_p(shifts.data_ptr()),
+                pt.ptycho.current_stream()))
         torch.cuda.synchronize()
     print("prof done")
 
