@@ -1,5 +1,7 @@
 """Kernel-level timing of every pass (CUDA events, device-resident inputs) next to the reference's
-cuFFT path on the same GPU.  Development tool; the judged numbers come from bench.py."""
+cuFFT path on the same GPU (oracle/_ref -- which is why this lives under tests/: only tests/, smoke()
+and bench.py may execute anything from oracle/).  Development tool; the judged numbers come from
+bench.py.   usage: python tests/tools/kbench.py <ndet> <angles> [<modes> [poisson]]"""
 import ctypes
 import os
 import sys
@@ -8,7 +10,7 @@ import time
 import numpy as np
 import torch
 
-ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 sys.path.insert(0, ROOT)
 sys.path.insert(0, os.path.join(ROOT, "libtike-cufft_b200"))
 import workloads  # noqa: E402
