@@ -127,11 +127,19 @@ int ptx_cg_grad(ptx_plan* p, int what, const void* psi, const void* scan, const 
  * given, obj_a / prb_a are not transformed again (skipped positions read as 0).
  * want_ab != 0: additionally cost[5+c] += sum sqrt(I_c data) and cost[10+c] += sum I_c for the five
  * intensities I_c evaluated (c = 0: p1), i.e. the a and b of ptycho.py:342-343 that the NEXT
- * iteration would compute from the accepted candidate; cost then is 16 doubles. */
+ * iteration would compute from the accepted candidate; cost then is 16 doubles.
+ * p23_out (nullable): [T,S,N,N] pairs of floats, receives (p2, p3) of every pixel, from which
+ * ptx_cg_intensity_step forms the intensity after the accepted step without another transform. */
 int ptx_cg_linesearch(ptx_plan* p, const void* obj_a, const void* prb_a, int nmodes_a, int mode_a0,
                       const void* obj_b, const void* prb_b, int nmodes_b, int mode_b0, int npairs,
                       const void* scan, const float* data, const float* p1_in, const void* far_a,
-                      int model, int c0, int ncand, int want_ab, double* cost, void* stream);
+                      int model, int c0, int ncand, int want_ab, void* p23_out, double* cost,
+                      void* stream);
+
+/* inten[i] += step^2 * p23[i].p2 + step * p23[i].p3, i < n: sum_k |fwd(...)|^2 after moving `step`
+ * along the direction the last line search explored (ptycho.py:424-428 recomputes it with M more
+ * forward operators for every probe mode; |t1 + g t2|^2 = p1 + g^2 p2 + g p3 is the same number). */
+int ptx_cg_intensity_step(float* inten, const void* p23, size_t n, float step, void* stream);
 
 /* ---------------------------------------------------------------------------------------
  * Position correction (ptycho.py:163-248, called from the CG loop at ptycho.py:398-403).

@@ -112,6 +112,17 @@ __global__ void k_axpy_s(float2* __restrict__ y, const float2* __restrict__ x, s
   }
 }
 
+// I += g^2 p2 + g p3 : the intensity after a step g along the searched direction, from the (p2, p3)
+// the line search left behind (|t1 + g t2|^2 = |t1|^2 + g^2 |t2|^2 + 2 g Re(t1 conj t2))
+__global__ void k_inten_update(float* __restrict__ inten, const float2* __restrict__ p23, size_t n, float g) {
+  const float g2 = g * g;
+  for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n;
+       i += (size_t)gridDim.x * blockDim.x) {
+    const float2 v = __ldcs(p23 + i);
+    inten[i] += g2 * v.x + g * v.y;
+  }
+}
+
 __global__ void k_absmax(const float2* __restrict__ x, size_t n, float* out) {
   float m = 0.f;
   for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n;
@@ -530,7 +541,8 @@ int ptx_cg_grad(ptx_plan* p, int what, const void* psi, const void* scan, const 
 int ptx_cg_linesearch(ptx_plan* p, const void* obj_a, const void* prb_a, int nmodes_a, int mode_a0,
                       const void* obj_b, const void* prb_b, int nmodes_b, int mode_b0, int npairs,
                       const void* scan, const float* data, const float* p1_in, const void* far_a,
-                      int model, int c0, int ncand, int want_ab, double* cost, void* stream) {
+                      int model, int c0, int ncand, int want_ab, void* p23_out, double* cost,
+                      void* stream) {
   int rc = check_plan(p);
   if (rc) return rc;
   if (!obj_a || !prb_a || !obj_b || !prb_b || !scan || !data || !cost || npairs < 1 || ncand < 1 ||
@@ -552,6 +564,7 @@ int ptx_cg_linesearch(ptx_plan* p, const void* obj_a, const void* prb_a, int nmo
   a.inten_in = p1_in;
   a.far_in = (const float2*)far_a;
   a.far_ms = p->ptheta * p->nscan * p->ndet * p->ndet;
+  a.p23 = (float2*)p23_out;
   a.npairs = npairs;
   a.c0 = c0;
   a.ncand = ncand;
@@ -718,6 +731,14 @@ int ptx_prepare_data(const float* raw, const long long* ids, size_t nsel, size_t
 static int vec_grid(size_t n) {
   size_t b = (n + 255) / 256;
   return (int)(b < 1 ? 1 : (b > 1184 ? 1184 : b));
+}
+
+int ptx_cg_intensity_step(float* inten, const void* p23, size_t n, float step, void* stream) {
+  if (!inten || !p23) return fail(PTX_EINVAL, "ptx_cg_intensity_step: null array");
+  k_inten_update<<<vec_grid(n), 256, 0, (cudaStream_t)stream>>>(inten, (const float2*)p23, n, step);
+  g_launches.fetch_add(1);
+  CUDA_TRY(cudaGetLastError());
+  return PTX_OK;
 }
 
 int ptx_vec_dai_yuan_reduce(const void* g, const void* g0, const void* d, size_t n, double* red,

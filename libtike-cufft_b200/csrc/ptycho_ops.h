@@ -35,6 +35,7 @@ struct PassArgs {
   float2* far;              // [T,S,N,N] (k_fwd output; k_grad: optional far-field cache, pre-residual)
   const float2* far_in;     // k_adj input; k_linesearch: optional cached first far field of every pair
   size_t far_ms;            // complex elements between modes (pairs) of the cache
+  float2* p23;              // k_linesearch: optional [T,S,N,N] output of (p2, p3) per pixel
   float2* grad;  // object gradient [T,nz,n] or probe gradient base (angle stride grad_ts)
   size_t grad_ts;
   const float* sc;  // device scalars

@@ -479,6 +479,7 @@ __global__ void __launch_bounds__(P::NT) k_linesearch(const PassArgs a,
     const int t = pat / g.S;
     const Pat p = make_pat(a.scan, pat, g);
     const float* p1in = a.inten_in ? a.inten_in + (size_t)pat * NN : nullptr;
+    float2* p23o = a.p23 ? a.p23 + (size_t)pat * NN : nullptr;  // (p2, p3): intensity at any step later
     const float2* psi_a = a.psi + (size_t)t * g.nz * g.n;
     const float2* psi_b = a.psi_b + (size_t)t * g.nz * g.n;
     for (int j = 0; j < a.npairs; ++j) {
@@ -566,6 +567,7 @@ __global__ void __launch_bounds__(P::NT) k_linesearch(const PassArgs a,
                   const float dd = c.dbuf[data_index<P>(c, e)];
                   const float sqd = fsqrt(dd);
                   if (p1in) q1 = __ldg(p1in + spec_index<P>(c, k1, e));
+                  if (p23o) __stcg(p23o + spec_index<P>(c, k1, e), make_float2(q2, q3));
                   float gam = gam0;
                   if (AB) {
                     cost[0] += minf_ab_px<MODEL>(q1, dd, sqd, sab[0], sab[5]);

@@ -310,6 +310,10 @@ class CGPtychoSolver(PtychoCuFFT):
     #: iteration (ptycho.py:330-343) from the probe line search, which has just evaluated exactly
     #: that intensity, instead of running the intensity pass again
     reuse_line_search_sums = True
+    #: several modes with probe recovery: after the probe line search of mode m, form the summed
+    #: intensity that mode m + 1 starts from as I + g^2 p2 + g p3 (one pass over the intensity map)
+    #: instead of M forward operators (ptycho.py:424-428)
+    incremental_intensity = True
     #: diagnostics hook used by the parity tests: a list of raw line-search results, consumed in call
     #: order, that override the solver's own decisions (the costs are still evaluated and logged)
     _forced_steps = None
@@ -362,7 +366,7 @@ class CGPtychoSolver(PtychoCuFFT):
                               _ptr(far_out) if far_out is not None else None, current_stream()))
 
     def _line_search(self, obj_a, prb_a, nm_a, m_a, obj_b, prb_b, nm_b, m_b, npairs, scan, data,
-                     p1, model, far_a=None, want_ab=False):
+                     p1, model, far_a=None, want_ab=False, p23=None):
         """Fused line_search_sqr: evaluates `ls_candidates` halvings per pass (ptycho.py:272-281).
         `far_a`: [npairs, T,S,N,N] cached first far fields (see `_grad(far_out=...)`).
         `want_ab`: also reduce a = sum sqrt(I data), b = sum I for every candidate intensity; after
@@ -387,7 +391,8 @@ class CGPtychoSolver(PtychoCuFFT):
                                         _ptr(prb_b), nm_b, m_b, npairs, _ptr(scan), _ptr(data),
                                         _ptr(p1) if p1 is not None else None,
                                         _ptr(far_a) if far_a is not None else None, model, c0, K,
-                                        1 if want_ab else 0, _ptr(cost), current_stream()))
+                                        1 if want_ab else 0, _ptr(p23) if p23 is not None else None,
+                                        _ptr(cost), current_stream()))
             c = self._sum(cost).cpu().numpy()
             self.ls_log.append((c0, c[:1 + K].copy()))
             if forced is not None and (forced == 0 or forced >= 2.0 ** -(c0 + K - 1)):
@@ -530,6 +535,8 @@ class CGPtychoSolver(PtychoCuFFT):
         # F(psi, probe_k) of the gradient passes, re-read by the line searches that follow them
         far = (torch.empty((M,) + tuple(data.shape), dtype=torch.complex64, device=dev)
                if self.cache_far_field else None)
+        p23 = (torch.empty(tuple(data.shape) + (2,), dtype=torch.float32, device=dev)
+               if (multi and recover_prb and self.incremental_intensity) else None)
         sum_data = float(self._sum(data.sum(dtype=torch.float64).reshape(1))) if mdl == 0 else 0.0
 
         gradpsi = torch.zeros_like(psi)
@@ -604,7 +611,7 @@ class CGPtychoSolver(PtychoCuFFT):
             if recover_prb:
                 for m in range(M):
                     # 2) probe retrieval subproblem with fixed object (ptycho.py:420-441)
-                    if multi:
+                    if multi and not (m > 0 and p23 is not None):
                         self._intensity(psi, scan, probe, data, inten, mdl)
                     kg = (float(M) if mdl == 0 else 1.0) / S      # Q13: * nmodes only for gaussian
                     check(lib.ptx_cg_prep_gscale(_ptr(self._absmax(psi)), kg, _ptr(sc_prb),
@@ -620,9 +627,12 @@ class CGPtychoSolver(PtychoCuFFT):
                     gammaprb = 0.5 * self._line_search(psi, probe, M, m, psi, dprb[m], 1, 0, 1,
                                                        scan, data, inten, mdl,
                                                        far_a=far[m] if far is not None else None,
-                                                       want_ab=reuse)
+                                                       want_ab=reuse, p23=p23)
                     if reuse and self._ls_ab is not None:
                         carried = [float(x) for x in self._ls_ab]
+                    if p23 is not None and m + 1 < M:  # the intensity mode m + 1 will start from
+                        check(lib.ptx_cg_intensity_step(_ptr(inten), _ptr(p23), inten.numel(),
+                                                        float(gammaprb), current_stream()))
                     # update probe (ptycho.py:463)
                     if T == 1:
                         self._axpy(probe[0, m], dprb[m, 0], gammaprb)

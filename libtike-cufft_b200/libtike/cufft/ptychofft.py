@@ -38,7 +38,8 @@ SYMBOLS = [
     ("ptx_cg_intensity", _i, [_vp, _vp, _vp, _vp, _i, _fp, _fp, _fp, _i, _dp, _vp]),
     ("ptx_cg_grad", _i, [_vp, _i, _vp, _vp, _vp, _i, _i, _fp, _fp, _fp, _i, _vp, _sz, _vp, _vp]),
     ("ptx_cg_linesearch", _i, [_vp, _vp, _vp, _i, _i, _vp, _vp, _i, _i, _i, _vp, _fp, _fp, _vp, _i, _i,
-                               _i, _i, _dp, _vp]),
+                               _i, _i, _vp, _dp, _vp]),
+    ("ptx_cg_intensity_step", _i, [_fp, _vp, _sz, ctypes.c_float, _vp]),
     ("ptx_register_translation", _i, [_vp, _vp, _vp, _sz, _i, _i, _dp, _vp]),
     ("ptx_cg_position_shifts", _i, [_vp, _vp, _vp, _vp, _i, _dp, _vp]),
     ("ptx_prepare_data", _i, [_fp, _vp, _sz, _sz, ctypes.c_float, _i, _fp, _vp]),

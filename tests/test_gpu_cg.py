@@ -348,3 +348,26 @@ def test_cg_shortcuts_do_not_change_results(model, ndet):
     e = (rel_l2(res[True][0]["psi"], res[False][0]["psi"]), rel_l2(res[True][0]["probe"], res[False][0]["probe"]))
     print("shortcuts on vs off: psi %.2e probe %.2e" % e)
     assert max(e) < 1e-5
+
+
+@pytest.mark.parametrize("model,nmodes", [("gaussian", 3), ("poisson", 2)])
+def test_cg_incremental_intensity_multi_mode(model, nmodes):
+    """Several probe modes: the summed intensity that mode m + 1 of the probe phase starts from is
+    formed as I + g^2 p2 + g p3 from mode m's line search instead of M forward operators
+    (incremental_intensity).  Against the same solver recomputing it, position correction on."""
+    pt = _pt()
+    data, psi0, scan, prb0 = _problem(nmodes, 40, model, 128 if model == "gaussian" else 64)
+    ndet = data.shape[-1]
+    nscan = scan.shape[1]
+    nz, n = psi0.shape[1:]
+    res = {}
+    for fast in (False, True):
+        with pt.CGPtychoSolver(nscan, ndet, ndet, 1, nz, n) as slv:
+            slv.incremental_intensity = fast
+            res[fast] = (slv.run_batch(data, psi0, scan, prb0, piter=5, model=model, recover_prb=True),
+                         list(slv.history))
+    sig = lambda hist: [tuple(x if x > 1e-6 else 0.0 for x in h[1:]) for h in hist]  # noqa: E731
+    assert sig(res[True][1]) == sig(res[False][1])
+    e = (rel_l2(res[True][0]["psi"], res[False][0]["psi"]), rel_l2(res[True][0]["probe"], res[False][0]["probe"]))
+    print("incremental intensity on vs off: psi %.2e probe %.2e" % e)
+    assert max(e) < 1e-5

@@ -72,7 +72,7 @@ def main(ndet=128, T=4, nside=32, nmodes=1, model=0):
             check(lib.ptx_cg_linesearch(slv._h, ctypes.c_void_p(psi1.data_ptr()), ctypes.c_void_p(probe.data_ptr()),
                                         nmodes, 0, ctypes.c_void_p(dpsi.data_ptr()), ctypes.c_void_p(probe.data_ptr()),
                                         nmodes, 0, nmodes, ctypes.c_void_p(scan.data_ptr()),
-                                        ctypes.c_void_p(data.data_ptr()), None, None, model, 0, 4, 0,
+                                        ctypes.c_void_p(data.data_ptr()), None, None, model, 0, 4, 0, None,
                                         ctypes.c_void_p(cost.data_ptr()), current_stream()))
         rows.append(("cg_linesearch (2 FFT/mode, 4 candidates)", timeit(ls)))
         far = torch.empty((nmodes,) + tuple(data.shape), dtype=torch.complex64, device="cuda")
@@ -84,7 +84,7 @@ def main(ndet=128, T=4, nside=32, nmodes=1, model=0):
                                         nmodes, 0, ctypes.c_void_p(dpsi.data_ptr()), ctypes.c_void_p(probe.data_ptr()),
                                         nmodes, 0, nmodes, ctypes.c_void_p(scan.data_ptr()),
                                         ctypes.c_void_p(data.data_ptr()), None, ctypes.c_void_p(far.data_ptr()),
-                                        model, 0, 4, 0, ctypes.c_void_p(cost.data_ptr()), current_stream()))
+                                        model, 0, 4, 0, None, ctypes.c_void_p(cost.data_ptr()), current_stream()))
         rows.append(("cg_linesearch, first far field cached", timeit(ls_cached)))
         rows.append(("cg_grad object + far-field cache write", timeit(
             lambda: slv._grad(0, psi1, scan, probe, 0, data, None, 1.0, 1.0, 1.0, model, gradpsi, far_out=far[0]))))
