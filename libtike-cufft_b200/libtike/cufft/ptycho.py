@@ -555,7 +555,7 @@ class CGPtychoSolver(PtychoCuFFT):
               "iteration, step size object, step size probe, function min")  # csv column headers
         gammaprb = 0
         carried = None
-        reuse = bool(self.reuse_line_search_sums) and M == 1 and recover_prb
+        reuse = bool(self.reuse_line_search_sums) and recover_prb and (M == 1 or p23 is not None)
         self.history = []  # (iteration, step size object, step size probe) -- diagnostics only
         self.ls_log = []   # (first candidate exponent, [f(0), f(2^-c0), ...]) per fused pass
         self.shift_log = []  # device [S,2] float64 shifts of every position-correction step
@@ -627,10 +627,12 @@ class CGPtychoSolver(PtychoCuFFT):
                     gammaprb = 0.5 * self._line_search(psi, probe, M, m, psi, dprb[m], 1, 0, 1,
                                                        scan, data, inten, mdl,
                                                        far_a=far[m] if far is not None else None,
-                                                       want_ab=reuse, p23=p23)
-                    if reuse and self._ls_ab is not None:
-                        carried = [float(x) for x in self._ls_ab]
-                    if p23 is not None and m + 1 < M:  # the intensity mode m + 1 will start from
+                                                       want_ab=reuse and m == M - 1, p23=p23)
+                    # a, b, cost of the intensity the NEXT iteration opens with: only the last mode's
+                    carried = ([float(x) for x in self._ls_ab]
+                               if (reuse and m == M - 1 and self._ls_ab is not None) else None)
+                    if p23 is not None and (m + 1 < M or carried is not None):
+                        # the intensity mode m + 1 (or the next iteration) will start from
                         check(lib.ptx_cg_intensity_step(_ptr(inten), _ptr(p23), inten.numel(),
                                                         float(gammaprb), current_stream()))
                     # update probe (ptycho.py:463)
