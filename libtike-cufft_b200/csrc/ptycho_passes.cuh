@@ -394,7 +394,7 @@ __global__ void __launch_bounds__(P::NT) k_grad(const PassArgs a, const __grid_c
     auto residual = [&](int k1, float2(&v)[P::E]) {
       if (CACHE) {  // keep F(psi, probe) for the line search that follows (ptycho.py:385, 457): 8 N^2 B
 #pragma unroll
-        for (int e = 0; e < P::E; ++e) __stcg(fc + spec_index<P>(c, k1, e), v[e]);
+        for (int e = 0; e < P::E; ++e) __stcs(fc + spec_index<P>(c, k1, e), v[e]);  // streaming: read back a pass later
       }
       dp_wait<P>(c);
 #pragma unroll
@@ -567,7 +567,7 @@ __global__ void __launch_bounds__(P::NT) k_linesearch(const PassArgs a,
                   const float dd = c.dbuf[data_index<P>(c, e)];
                   const float sqd = fsqrt(dd);
                   if (p1in) q1 = __ldg(p1in + spec_index<P>(c, k1, e));
-                  if (p23o) __stcg(p23o + spec_index<P>(c, k1, e), make_float2(q2, q3));
+                  if (p23o) __stcs(p23o + spec_index<P>(c, k1, e), make_float2(q2, q3));
                   float gam = gam0;
                   if (AB) {
                     cost[0] += minf_ab_px<MODEL>(q1, dd, sqd, sab[0], sab[5]);
