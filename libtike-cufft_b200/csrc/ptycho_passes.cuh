@@ -537,7 +537,7 @@ __global__ void __launch_bounds__(P::NT) k_linesearch(const PassArgs a,
                 if (t1c) {  // block-uniform
                   int dx, dy;
                   elem_offset<typename P::S2>(e, dx, dy);
-                  t1v[j] = t1p ? __ldcg(t1p + (P::RC * pos_to_freq_y<P>(dy) * P::N + pos_to_freq_x<P>(dx)))
+                  t1v[j] = t1p ? __ldcs(t1p + (P::RC * pos_to_freq_y<P>(dy) * P::N + pos_to_freq_x<P>(dx)))
                                : make_float2(0.f, 0.f);
                 } else {
                   t1v[j] = st[e * P::NT];

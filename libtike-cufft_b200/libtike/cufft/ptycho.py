@@ -379,6 +379,7 @@ class CGPtychoSolver(PtychoCuFFT):
         self._ls_ab = None
 
         def done(step, c):
+            self.ls_steps.append(step)
             if want_ab:
                 j = 0 if step == 0 else int(round(-np.log2(step))) - c0 + 2  # slot of step / 2
                 if 0 <= j <= 4:
@@ -558,6 +559,7 @@ class CGPtychoSolver(PtychoCuFFT):
         reuse = bool(self.reuse_line_search_sums) and recover_prb and (M == 1 or p23 is not None)
         self.history = []  # (iteration, step size object, step size probe) -- diagnostics only
         self.ls_log = []   # (first candidate exponent, [f(0), f(2^-c0), ...]) per fused pass
+        self.ls_steps = []  # raw result of every line search, in call order (replayable: _forced_steps)
         self.shift_log = []  # device [S,2] float64 shifts of every position-correction step
         for i in range(piter):
             # 1) object retrieval subproblem with fixed probes (ptycho.py:327-345).  a, b, the probe
