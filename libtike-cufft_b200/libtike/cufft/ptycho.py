@@ -534,10 +534,13 @@ class CGPtychoSolver(PtychoCuFFT):
         multi = M > 1
         inten = torch.empty_like(data) if multi else None
         # F(psi, probe_k) of the gradient passes, re-read by the line searches that follow them
+        # (both shortcuts are dropped, not shrunk, when their arrays would not fit comfortably)
+        free_bytes = torch.cuda.mem_get_info(dev)[0]
         far = (torch.empty((M,) + tuple(data.shape), dtype=torch.complex64, device=dev)
-               if self.cache_far_field else None)
+               if (self.cache_far_field and 8 * M * data.numel() < 0.4 * free_bytes) else None)
         p23 = (torch.empty(tuple(data.shape) + (2,), dtype=torch.float32, device=dev)
-               if (multi and recover_prb and self.incremental_intensity) else None)
+               if (multi and recover_prb and self.incremental_intensity
+                   and 8 * data.numel() < 0.2 * torch.cuda.mem_get_info(dev)[0]) else None)
         sum_data = float(self._sum(data.sum(dtype=torch.float64).reshape(1))) if mdl == 0 else 0.0
 
         gradpsi = torch.zeros_like(psi)
