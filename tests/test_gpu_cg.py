@@ -373,3 +373,32 @@ def test_cg_incremental_intensity_multi_mode(model, nmodes):
     e = (rel_l2(res[True][0]["psi"], res[False][0]["psi"]), rel_l2(res[True][0]["probe"], res[False][0]["probe"]))
     print("incremental intensity on vs off: psi %.2e probe %.2e" % e)
     assert max(e) < 1e-5
+
+
+def test_run_batch_chunks_trailing_angles_and_input_ownership():
+    """run_batch (ptycho.py:135-162): angles go through `run` in chunks of ptheta, the trailing
+    ntheta % ptheta angles come back untouched (Q9), the caller's psi / probe / scan are not
+    modified (copies; scan corrections stay on the device copy), and the pipelined chunks land at
+    their own indices: each chunk equals a stand-alone run of the same angles."""
+    pt = _pt()
+    ndet, side, ntheta, T = 64, 3, 5, 2
+    w = workloads.synth_angles(ntheta, 150, 160, ndet, ndet, side, 1, seed0=31)
+    psi, scan, probe = w["psi"], w["scan"], w["probe"]
+    data = np.stack([np.abs(O.fwd(psi[t:t + 1], scan[t:t + 1], np.ascontiguousarray(probe[t:t + 1, 0]), ndet))[0] ** 2
+                     for t in range(ntheta)]).astype(np.float32)
+    psi0 = np.ones_like(psi)
+    prb0 = (probe * (0.9 + 0.1j)).astype(np.complex64)
+    keep = [x.copy() for x in (psi0, prb0, scan, data)]
+    with pt.CGPtychoSolver(side * side, ndet, ndet, T, 150, 160) as slv:
+        out = slv.run_batch(data, psi0, scan, prb0, piter=3, model="gaussian", recover_prb=True)
+        for a, b in zip((psi0, prb0, scan, data), keep):
+            assert np.array_equal(a, b)
+        # trailing angle (index 4) untouched
+        assert np.array_equal(out["psi"][4], psi0[4]) and np.array_equal(out["probe"][4], prb0[4])
+        for k in range(2):
+            ids = slice(k * T, (k + 1) * T)
+            one = slv.run_batch(data[ids], psi0[ids], scan[ids], prb0[ids], piter=3, model="gaussian",
+                                recover_prb=True)
+            assert rel_l2(out["psi"][ids], one["psi"]) < 1e-5
+            assert rel_l2(out["probe"][ids], one["probe"]) < 1e-5
+            assert rel_l2(out["psi"][ids], psi0[ids]) > 1e-3  # it did reconstruct something
