@@ -452,7 +452,10 @@ class CGPtychoSolver(PtychoCuFFT):
         if st is None or st["M"] != M:
             def pin(shape, dtype):
                 return torch.empty(shape, dtype=dtype).pin_memory()
-            st = {"M": M, "streams": [torch.cuda.Stream(), torch.cuda.Stream()], "slots": []}
+            # {fscale, iscale, gscale} = 1: made ONCE -- torch.tensor(..., device=) is a pageable, hence
+            # stream-synchronous, copy that would stall the host behind the chunk's 67 MB upload
+            st = {"M": M, "streams": [torch.cuda.Stream(), torch.cuda.Stream()], "slots": [],
+                  "sc": torch.ones(3, dtype=torch.float32, device=dev)}
             for _ in range(2):
                 st["slots"].append({
                     "h": (pin((T, self.nscan, self.ndet, self.ndet), torch.float32),
@@ -497,7 +500,7 @@ class CGPtychoSolver(PtychoCuFFT):
                     self._intensity(d_psi, d_scan, d_prb, d_data, slot["inten"], mdl)
                 for k in range(M):
                     self._grad(0, d_psi, d_scan, d_prb, k, d_data, slot["inten"], 1.0, 1.0, 1.0, mdl,
-                               slot["g"])
+                               slot["g"], sc=st["sc"])
                 slot["gh"].copy_(slot["g"], non_blocking=True)
                 slot["done"] = torch.cuda.Event()
                 slot["done"].record(stream)
