@@ -292,12 +292,15 @@ def run_b200(args, world, rank, local):
                     s1.position_correction = on
                     with contextlib.redirect_stdout(io.StringIO()):
                         s1.run(d1, psi[:1], scan[:1].clone(), probe[:1].clone(), piter=2, recover_prb=True)
-                        sc1 = scan[:1].clone()
-                        torch.cuda.synchronize()
-                        t0 = time.perf_counter()
-                        s1.run(d1, psi[:1], sc1, probe[:1].clone(), piter=16, recover_prb=True)
-                        torch.cuda.synchronize()
-                        dt = time.perf_counter() - t0
+                        dt = None
+                        for _ in range(2):  # best of two: a stray allocation stall once halved a run
+                            sc1, pr1 = scan[:1].clone(), probe[:1].clone()
+                            torch.cuda.synchronize()
+                            t0 = time.perf_counter()
+                            s1.run(d1, psi[:1], sc1, pr1, piter=16, recover_prb=True)
+                            torch.cuda.synchronize()
+                            t1 = time.perf_counter() - t0
+                            dt = t1 if dt is None else min(dt, t1)
                     cg[key] = 16 / dt
                     if on:  # it varies with the data: fused 4-candidate passes
                         cg["line_search_passes_per_iter"] = len(s1.ls_log) / 16.0
