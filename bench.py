@@ -1,36 +1,48 @@
 #!/usr/bin/env python
 """Headline benchmark: diffraction patterns/s through the fused fwd -> residual -> adj pass.
 
-    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl b200|reference] [--workload c2|c4]
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl b200|reference] [--workload c4|c2]
     python -m torch.distributed.run --nnodes=1 --nproc-per-node N --master-addr 127.0.0.1 \
         --master-port P bench.py --gpus N --steps K --warmup W
 
 A "step" is one pass of the hot path (a2 fwd + the Gaussian residual of
-ptycho.py:351-356 + a3 adj, i.e. the CG object gradient) over one batch of angles:
+ptycho.py:351-356 + a3 adj, i.e. the CG object gradient) over the WHOLE angle batch:
 
-  workload c2 (default; BASELINE.json configs[1]): per GPU 8 independent angles of a 512x512 object,
-      1024 scan positions each, 128x128 detector, 1 probe mode, Gaussian model -> 8192 patterns/step,
-      512 MiB of measured data per step (larger than the 126 MB L2, so no flush is needed);
-  workload c4 (configs[3]): 1024x1024 object slices, 256x256 detector, 1024 positions per angle.
+  workload c4 (default; BASELINE.json configs[3], the one north_star's targets are quoted on):
+      168 angles x 1024 scan positions, 1024x1024 object slices, 256x256 detector, 1 probe mode,
+      Gaussian model = 172 032 patterns and 45 GB of measured data per step.  The batch is FIXED:
+      N GPUs hold 168 / N angles each ("scaling": "strong"; N = 1 holds all 168 in one B200's HBM).
+  workload c2 (configs[1]): 8 angles x 1024 positions, 512x512 object, 128x128 detector per GPU.
+      Always measured as a sub-record (`workloads.c2`) of the default line.
 
-Angles are independent problems (ptheta = 1 semantics of every reference test), so N GPUs run N
-shards with no data-path collective: "scaling": "weak".
+Angles are independent problems (ptheta = 1 semantics of every reference test), so the shards need
+no data-path collective.  The only collective the path has -- the all-reduce of the CG scalars when
+ONE run spans GPUs -- is timed separately (`cg.coupled`) and checked against a single-GPU
+ptheta = 2 run (`cg.scalarcomm_check`) whenever N >= 2.
 
-  value    -- patterns/s with every input already resident in HBM (CUDA events, max over ranks)
-  e2e      -- the same pass through the host-array API (`CGPtychoSolver.grad_ptycho_batch`): pinned
-              host buffers in, host gradient out, H2D/D2H inside the timed region
-  roofline -- the fused kernel k_grad<.,gaussian,object>: algorithmic HBM bytes per launch / its
-              CUDA-event duration against MEASURED_PEAKS.json, plus the FP32-pipe view of the same
-              launches (this kernel is FP32-bound)
-  cpu_baseline -- the NumPy/pocketfft oracle on the box's host cores, bounded sample (rank 0, N = 1)
-  cg       -- CG iterations/s of `CGPtychoSolver.run` on one c2 angle (object + probe recovery)
+  value     patterns/s with every input resident in HBM (CUDA events, max over ranks)
+  e2e       the same pass through the host-array API (`CGPtychoSolver.grad_ptycho_batch`): host
+            buffers in, host gradient out, H2D / D2H inside the timed region; `value` with pinned
+            host arrays, `pageable` with ordinary NumPy arrays (what a drop-in caller holds)
+  e2e_cg    `run_batch(piter=8, recover_prb=True)` -- the reference's own host entry point
+            (ptycho.py:135-162) -- in angle-iterations/s through host arrays
+  roofline  the fused kernel k_grad<gaussian, object>: SURVEY.md section 8d says FP32-bound, so
+            achieved = algorithmic FFT flops per launch / CUDA-event launch time against the nominal
+            FP32 peak; the HBM view (algorithmic bytes against MEASURED_PEAKS.json) and the
+            L1/shared data-pipe view are sub-keys
+  cpu_baseline  the NumPy/pocketfft oracle on the box's host cores, bounded sample (rank 0, N = 1)
+  cg        CG iterations/s of `CGPtychoSolver.run` (object + probe recovery), per workload
+  workloads c2, the 5-mode C3 shape and the C5 Poisson detector sweep, same pass
 
 --impl reference runs the REFERENCE's own CUDA/cuFFT operators (oracle/_ref, compiled unmodified
 from /root/reference/src/cuda) for the same pass and config: fwd -> torch elementwise (the CuPy
-statements of ptycho.py:351-356) -> adj.  The reference has no CPU implementation of this path;
-if oracle/_ref did not travel, the NumPy port is timed instead and the line says so.
+statements of ptycho.py:351-356) -> adj, batched at ptheta = 21 angles per call.  The reference has
+no CPU implementation of this path; if oracle/_ref did not travel, the NumPy port is timed instead
+and the line says so.  Rank 0 alone runs it; each step is a bounded 21-angle sample of the batch.
 """
 import argparse
+import contextlib
+import io
 import json
 import os
 import sys
@@ -49,6 +61,11 @@ import torch  # noqa: E402
 import workloads  # noqa: E402
 
 FP32_NOMINAL_TFLOPS = 148 * 128 * 2 * 1.965e9 / 1e12  # 74.4, SURVEY.md section 8d
+C4_ANGLES = 168
+REF_ANGLES = 21   # angles per step (and per call) of the reference arm
+E2E_ANGLES = 21   # host-array legs: at most this many angles per rank (5.6 GB of pinned data at c4)
+CG_ANGLES = 4     # e2e_cg / sharded CG: angles per rank
+CG_ITERS = 8
 
 
 def peaks():
@@ -113,16 +130,42 @@ def physical_gpu_index(local):
     return local
 
 
-def make_workload(name, angles):
-    if name == "c2":
-        w = workloads.c2_single_angle(ntheta=angles)
-        label = "c2: %d angles/GPU x 1024 positions, 512x512 object, 128x128 detector, 1 mode, gaussian" % angles
-    elif name == "c4":
-        w = workloads.c4_catalyst(angles)
-        label = "c4: %d angles/GPU x 1024 positions, 1024x1024 object, 256x256 detector, 1 mode, gaussian" % angles
-    else:
-        raise SystemExit("unknown workload " + name)
-    return w, label
+# ---------------------------------------------------------------------------------------------
+# workloads and the config record (ONE function for both arms: the dicts must be identical)
+# ---------------------------------------------------------------------------------------------
+def total_angles(name, world):
+    return C4_ANGLES if name == "c4" else 8 * world
+
+
+def make_config(name, world):
+    if name == "c4":
+        return {"workload": "c4: 168 angles x 1024 positions, 1024x1024 object slices, 256x256 detector, "
+                            "1 mode, gaussian (BASELINE.json configs[3])",
+                "patterns_per_step": C4_ANGLES * 1024,
+                "angles_per_gpu": C4_ANGLES // world,
+                "l2": "45 GB of measured data per step (>> 126 MB L2): no flush needed",
+                "parallelism": "angle shards (168 / N per GPU), no data-path collective"}
+    return {"workload": "c2: 8 angles/GPU x 1024 positions, 512x512 object, 128x128 detector, 1 mode, "
+                        "gaussian (BASELINE.json configs[1])",
+            "patterns_per_step": 8 * world * 1024,
+            "angles_per_gpu": 8,
+            "l2": "537 MB of measured data per GPU and step (> 126 MB L2): no flush needed",
+            "parallelism": "angle shards (8 per GPU), no data-path collective"}
+
+
+def shard(name, world, rank):
+    """(first global angle, number of angles) of this rank."""
+    if name == "c4":
+        per = C4_ANGLES // world
+        return rank * per, per
+    return rank * 8, 8
+
+
+def make_angles(name, first, count):
+    """Seeded inputs of `count` angles starting at global angle `first` (seed = angle index)."""
+    if name == "c4":
+        return workloads.synth_angles(count, 1024, 1024, 256, 256, 32, 1, seed0=first)
+    return workloads.synth_angles(count, 512, 512, 128, 128, 32, 1, seed0=first)
 
 
 def algorithmic_bytes(w, T):
@@ -169,21 +212,35 @@ def max_over_ranks(x, world):
     return float(t.item())
 
 
-def timed_steps(step, steps, warmup, world, per_launch_events=False):
+def timed_steps(step, steps, warmup, world):
     """W warm-ups, then exactly K steps between barrier+synchronize, timed with CUDA events on the
-    launching stream; returns (seconds max over ranks, list of per-step ms on this rank)."""
+    launching stream; returns seconds (max over ranks)."""
     for _ in range(warmup):
         step()
     barrier(world)
-    evs = [torch.cuda.Event(enable_timing=True) for _ in range(steps + 1)]
-    evs[0].record()
-    for i in range(steps):
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(steps):
         step()
-        evs[i + 1].record()
+    e1.record()
     barrier(world)
-    total_ms = evs[0].elapsed_time(evs[-1])
-    per = [evs[i].elapsed_time(evs[i + 1]) for i in range(steps)]
-    return max_over_ranks(total_ms, world) * 1e-3, per
+    return max_over_ranks(e0.elapsed_time(e1), world) * 1e-3
+
+
+def wall_steps(step, steps, warmup, world):
+    """Host-clock variant for the legs whose work includes host-side copies."""
+    for _ in range(warmup):
+        step()
+    barrier(world)
+    t0 = time.perf_counter()
+    for _ in range(steps):
+        step()
+    barrier(world)
+    return max_over_ranks(time.perf_counter() - t0, world)
+
+
+def pinned(a):
+    return torch.from_numpy(np.ascontiguousarray(a)).pin_memory().numpy()
 
 
 def cpu_port_rate(w, seconds_target=12.0):
@@ -207,138 +264,313 @@ def cpu_port_rate(w, seconds_target=12.0):
     return reps * ns / dt, "%d x %d patterns of one angle (%.1f s)" % (reps, ns, dt)
 
 
+def quiet():
+    return contextlib.redirect_stdout(io.StringIO())
+
+
+# ---------------------------------------------------------------------------------------------
+# this repository's arm
+# ---------------------------------------------------------------------------------------------
+def synth_data(slv, psi, scan, probe, chunk=8):
+    """|fwd|^2 summed over modes, angle chunks of `chunk` (bounds the temporary far field)."""
+    import libtike.cufft as pt
+    T, S, N = psi.shape[0], scan.shape[1], slv.ndet
+    data = torch.empty((T, S, N, N), dtype=torch.float32, device=psi.device)
+    for t0 in range(0, T, chunk):
+        t1 = min(T, t0 + chunk)
+        with pt.PtychoCuFFT(S, slv.nprb, N, t1 - t0, slv.nz, slv.n) as op:
+            acc = None
+            for k in range(probe.shape[1]):
+                f = op.fwd(psi[t0:t1].contiguous(), scan[t0:t1].contiguous(),
+                           probe[t0:t1, k].contiguous()).abs().square_()
+                acc = f if acc is None else acc.add_(f)
+            data[t0:t1] = acc
+    return data
+
+
+def grad_rate(pt, w, T, steps, warmup, world=1, model=0, counts=0.0):
+    """Device-resident rate of the fused gradient pass on workload dict `w` (T angles): returns
+    (patterns/s on this rank, mean launch seconds of the dominant kernel, launches per step)."""
+    from libtike.cufft.ptychofft import launch_count
+    dev = torch.device("cuda", torch.cuda.current_device())
+    S, N, nz, n, M = w["nscan"], w["ndet"], w["nz"], w["n"], w["nmodes"]
+    psi_true, scan, probe = (torch.from_numpy(w[k]).to(dev) for k in ("psi", "scan", "probe"))
+    with pt.CGPtychoSolver(S, w["nprb"], N, T, nz, n) as slv:
+        data = synth_data(slv, psi_true, scan, probe)
+        if counts:
+            data = torch.poisson(data * (counts / data.mean())).contiguous()
+        psi = torch.ones_like(psi_true)
+        grad = torch.zeros_like(psi)
+        inten = torch.empty_like(data) if M > 1 else None
+        sc = torch.ones(3, dtype=torch.float32, device=dev)
+
+        def step():
+            grad.zero_()
+            if M > 1:
+                slv._intensity(psi, scan, probe, data, inten, model)
+            for k in range(M):
+                slv._grad(0, psi, scan, probe, k, data, inten, 1.0, 1.0, 1.0, model, grad, sc=sc)
+
+        for _ in range(warmup):
+            step()
+        torch.cuda.synchronize()
+        l0 = launch_count()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(steps):
+            step()
+        e1.record()
+        e1.synchronize()
+        secs = e0.elapsed_time(e1) * 1e-3
+        launches = (launch_count() - l0) // steps
+    return T * S * steps / secs, secs / steps, launches
+
+
+def cg_rates(pt, w, data1, psi1, scan1, probe1, iters=16):
+    """CG iterations/s of one device-resident angle, position correction on (the reference's
+    behaviour) and off; best of two runs each."""
+    S, N, nz, n = w["nscan"], w["ndet"], w["nz"], w["n"]
+    out = {"iters": iters, "recover_prb": True}
+    with pt.CGPtychoSolver(S, w["nprb"], N, 1, nz, n) as s1:
+        for key, on in (("iters_per_s", True), ("iters_per_s_no_position_correction", False)):
+            s1.position_correction = on
+            with quiet():
+                s1.run(data1, psi1, scan1.clone(), probe1.clone(), piter=2, recover_prb=True)
+                dt = None
+                for _ in range(2):
+                    sc1, pr1 = scan1.clone(), probe1.clone()
+                    torch.cuda.synchronize()
+                    t0 = time.perf_counter()
+                    s1.run(data1, psi1, sc1, pr1, piter=iters, recover_prb=True)
+                    torch.cuda.synchronize()
+                    t1 = time.perf_counter() - t0
+                    dt = t1 if dt is None else min(dt, t1)
+            out[key] = iters / dt
+            if on:
+                out["line_search_passes_per_iter"] = len(s1.ls_log) / float(iters)
+    return out
+
+
+def scalarcomm_check(pt, world, rank):
+    """2 ranks x 1 angle with a ScalarComm == 1 rank with ptheta = 2 (the NCCL all-reduce of the CG
+    scalars), on ranks 0 and 1; returns the record on rank 0."""
+    import torch.distributed as dist
+    from libtike.cufft.dist import ScalarComm
+    from oracle import numpy_ptycho as O  # noqa: F401  (not used: the check is product vs product)
+    w = workloads.synth_angles(2, 200, 220, 64, 64, 5, 1, seed0=11)
+    dev = torch.device("cuda", torch.cuda.current_device())
+    psi_t, scan, probe = (torch.from_numpy(w[k]).to(dev) for k in ("psi", "scan", "probe"))
+    with pt.PtychoCuFFT(25, 64, 64, 2, 200, 220) as op:
+        data = op.fwd(psi_t, scan, probe[:, 0].contiguous()).abs().square_().contiguous()
+    probe = probe * (0.9 + 0.1j)
+    probe[1] *= 1.3
+    psi0 = torch.ones_like(psi_t)
+    group = dist.new_group([0, 1])
+    rec = None
+    if rank < 2:
+        sl = slice(rank, rank + 1)
+        with pt.CGPtychoSolver(25, 64, 64, 1, 200, 220) as slv, quiet():
+            slv.comm = ScalarComm(group)
+            res = slv.run(data[sl].contiguous(), psi0[sl].contiguous(), scan[sl].clone(),
+                          probe[sl].clone(), piter=4, recover_prb=True)
+            calls, hist = slv.comm.calls, list(slv.history)
+        both = [torch.zeros_like(psi0[:1]) for _ in range(2)]
+        dist.all_gather(both, res["psi"].contiguous(), group=group)
+        if rank == 0:
+            with pt.CGPtychoSolver(25, 64, 64, 2, 200, 220) as slv, quiet():
+                want = slv.run(data, psi0, scan.clone(), probe.clone(), piter=4, recover_prb=True)
+                same_steps = list(slv.history) == hist
+            err = float(torch.linalg.norm(torch.cat(both) - want["psi"]) / torch.linalg.norm(want["psi"]))
+            rec = {"rel_l2_psi_vs_ptheta2": err, "same_step_decisions": bool(same_steps),
+                   "allreduces": int(calls), "ok": bool(err < 1e-5 and same_steps), "backend": "nccl"}
+    dist.barrier()
+    return rec
+
+
+def coupled_cg(pt, w, data, psi, scan, probe, world, iters=CG_ITERS):
+    """ONE run spanning all ranks (one angle each, CG scalars all-reduced over NCCL): iterations/s."""
+    from libtike.cufft.dist import ScalarComm
+    S, N, nz, n = w["nscan"], w["ndet"], w["nz"], w["n"]
+    with pt.CGPtychoSolver(S, w["nprb"], N, 1, nz, n) as slv, quiet():
+        slv.comm = ScalarComm()
+        slv.run(data[:1], psi[:1], scan[:1].clone(), probe[:1].clone(), piter=2, recover_prb=True)
+        c0 = slv.comm.calls
+        barrier(world)
+        t0 = time.perf_counter()
+        slv.run(data[:1], psi[:1], scan[:1].clone(), probe[:1].clone(), piter=iters, recover_prb=True)
+        barrier(world)
+        dt = max_over_ranks(time.perf_counter() - t0, world)
+        calls = slv.comm.calls - c0
+    return {"iters_per_s": iters / dt, "angles": world, "allreduces_per_iter": calls / float(iters),
+            "note": "one CG run over %d angles, one per GPU; sums / maxima of every phase all-reduced" % world}
+
+
 def run_b200(args, world, rank, local):
     import libtike.cufft as pt
     from libtike.cufft.ptychofft import launch_count
-    T = args.angles
-    w, label = make_workload(args.workload, T)
+    first, T = shard(args.workload, world, rank)
+    w = make_angles(args.workload, first, T)
     S, N, nz, n = w["nscan"], w["ndet"], w["nz"], w["n"]
     npat = T * S
     dev = torch.device("cuda", torch.cuda.current_device())
     psi_true, scan, probe = (torch.from_numpy(w[k]).to(dev) for k in ("psi", "scan", "probe"))
     hbm, peak_src = peaks()
+    extra = {}
     with pt.CGPtychoSolver(S, w["nprb"], N, T, nz, n) as slv:
-        data = slv.fwd(psi_true, scan, probe[:, 0]).abs().square_().contiguous()  # synthetic measurement
-        psi = torch.ones_like(psi_true)  # the solver's starting point (tests/test.py:55)
+        data = synth_data(slv, psi_true, scan, probe)   # synthetic measurement
+        psi = torch.ones_like(psi_true)                 # the solver's starting point (tests/test.py:55)
         grad = torch.zeros_like(psi)
+        sc = torch.ones(3, dtype=torch.float32, device=dev)
 
         def step():
             grad.zero_()
-            slv._grad(0, psi, scan, probe, 0, data, None, 1.0, 1.0, 1.0, 0, grad)
+            slv._grad(0, psi, scan, probe, 0, data, None, 1.0, 1.0, 1.0, 0, grad, sc=sc)
 
         sampler = ClockSampler(physical_gpu_index(local))
-        l0 = launch_count()
         for _ in range(args.warmup):
             step()
         barrier(world)
         sampler.start()
         l1 = launch_count()
-        secs, _ = timed_steps(step, args.steps, 0, world)
+        secs = timed_steps(step, args.steps, 0, world)
         launches = launch_count() - l1
         clocks = sampler.stop()
-        value = world * npat * args.steps / secs
+        value = total_angles(args.workload, world) * S * args.steps / secs
 
         # dominant kernel alone: events straight around each launch (same stream)
         kt = []
-        for _ in range(args.steps):
+        for _ in range(min(args.steps, 10)):
             grad.zero_()
             e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
             e0.record()
-            slv._grad(0, psi, scan, probe, 0, data, None, 1.0, 1.0, 1.0, 0, grad)
+            slv._grad(0, psi, scan, probe, 0, data, None, 1.0, 1.0, 1.0, 0, grad, sc=sc)
             e1.record()
             e1.synchronize()
             kt.append(e0.elapsed_time(e1) * 1e-3)
         kavg = float(np.mean(kt))
-        abytes, aflops = algorithmic_bytes(w, T), algorithmic_flops(w, T)
-        # the roof that binds: bytes this algorithm moves through the SM's
-        # 128 B/clk L1 / shared-memory pipe -- 2 exchanges x 2 transforms x (store + load) of the
-        # 8 N^2-byte tile, 4 bilinear taps + 2 probe reads + scatter staging and reductions
-        pipe_bytes = npat * N * N * 8 * (8 + 4 + 2 + 3.1)
-        pipe_peak = 148 * 128 * 1.965e9
-        pipe = {"achieved_tbs": pipe_bytes / kavg / 1e12, "peak_tbs": pipe_peak / 1e12,
-                "frac": pipe_bytes / kavg / pipe_peak,
-                "note": "L1/shared data pipe, 128 B/clk/SM x 148 SMs x 1.965 GHz; ncu "
-                        "l1tex__data_pipe_lsu_wavefronts reads 58 % busy (profiles/)"}
+    abytes, aflops = algorithmic_bytes(w, T), algorithmic_flops(w, T)
 
-        # end to end through the host-array API (pinned host memory in, host gradient out)
-        h = {k: torch.from_numpy(np.ascontiguousarray(v)).pin_memory().numpy()
-             for k, v in (("data", data.cpu().numpy()), ("psi", psi.cpu().numpy()),
-                          ("scan", w["scan"]), ("probe", w["probe"]))}
-        with pt.CGPtychoSolver(S, w["nprb"], N, 1, nz, n) as s1:
+    # ---- end to end through the host-array API: E angles of this rank's shard
+    E = min(T, E2E_ANGLES)
+    host = {"data": data[:E].cpu().numpy(), "psi": psi[:E].cpu().numpy(),
+            "scan": w["scan"][:E], "probe": w["probe"][:E]}
+    e2e = {}
+    with pt.CGPtychoSolver(S, w["nprb"], N, 1, nz, n) as s1:
+        for kind in ("pinned", "pageable"):
+            h = {k: (pinned(v) if kind == "pinned" else np.ascontiguousarray(v)) for k, v in host.items()}
+
             def e2e_step():
                 s1.grad_ptycho_batch(h["data"], h["psi"], h["scan"], h["probe"], model="gaussian")
-            for _ in range(max(1, min(args.warmup, 2))):
-                e2e_step()
-            barrier(world)
-            t0 = time.perf_counter()
-            for _ in range(args.steps):
-                e2e_step()
-            barrier(world)
-            e2e_secs = max_over_ranks(time.perf_counter() - t0, world)
-        h2d = sum(h[k].nbytes for k in h)
-        d2h = h["psi"].nbytes
+            dt = wall_steps(e2e_step, max(2, args.steps // 4), 1, world)
+            e2e[kind] = world * E * S * max(2, args.steps // 4) / dt
+            del h
+    h2d = sum(v.nbytes for v in host.values())
+    d2h = host["psi"].nbytes
 
-        cg = None
-        if rank == 0 and not args.no_cg:
-            with pt.CGPtychoSolver(S, w["nprb"], N, 1, nz, n) as s1:
-                import contextlib
-                import io
-                d1 = data[:1].contiguous()
-                cg = {"iters": 16, "recover_prb": True,
-                      "config": "one %s angle, device resident" % args.workload}
-                # position correction (ptycho.py:398-403) is unconditional in the reference: ON is
-                # the drop-in configuration; OFF is reported next to it
-                for key, on in (("iters_per_s", True), ("iters_per_s_no_position_correction", False)):
-                    s1.position_correction = on
-                    with contextlib.redirect_stdout(io.StringIO()):
-                        s1.run(d1, psi[:1], scan[:1].clone(), probe[:1].clone(), piter=2, recover_prb=True)
-                        dt = None
-                        for _ in range(2):  # best of two: a stray allocation stall once halved a run
-                            sc1, pr1 = scan[:1].clone(), probe[:1].clone()
-                            torch.cuda.synchronize()
-                            t0 = time.perf_counter()
-                            s1.run(d1, psi[:1], sc1, pr1, piter=16, recover_prb=True)
-                            torch.cuda.synchronize()
-                            t1 = time.perf_counter() - t0
-                            dt = t1 if dt is None else min(dt, t1)
-                    cg[key] = 16 / dt
-                    if on:  # it varies with the data: fused 4-candidate passes
-                        cg["line_search_passes_per_iter"] = len(s1.ls_log) / 16.0
+    # ---- the reference's host entry point: run_batch (ptycho.py:135-162), angle-iterations/s
+    C = min(T, CG_ANGLES)
+    with pt.CGPtychoSolver(S, w["nprb"], N, 1, nz, n) as s1, quiet():
+        hc = {k: v[:C] for k, v in host.items()}
+        s1.run_batch(hc["data"][:1], hc["psi"][:1], hc["scan"][:1], hc["probe"][:1], piter=2,
+                     recover_prb=True)
+        barrier(world)
+        t0 = time.perf_counter()
+        s1.run_batch(hc["data"], hc["psi"], hc["scan"], hc["probe"], piter=CG_ITERS, recover_prb=True)
+        barrier(world)
+        dt = max_over_ranks(time.perf_counter() - t0, world)
+    e2e_cg = {"value": world * C * CG_ITERS / dt, "unit": "angle-iterations/s",
+              "api": "CGPtychoSolver.run_batch(piter=%d, recover_prb=True), pageable host arrays" % CG_ITERS,
+              "sample": "%d angles per GPU" % C}
+    del host
+
+    # ---- CG iterations/s
+    cg = None
+    if rank == 0:
+        cg = cg_rates(pt, w, data[:1].contiguous(), psi[:1].contiguous(), scan[:1].contiguous(),
+                      probe[:1].contiguous())
+        cg["config"] = "one %s angle, device resident" % args.workload
+    if world > 1:
+        barrier(world)
+        coupled = coupled_cg(pt, w, data, psi, scan, probe, world)
+        check = scalarcomm_check(pt, world, rank)
+        if rank == 0:
+            cg["coupled"] = coupled
+            cg["scalarcomm_check"] = check
+    del data, grad, psi
+    torch.cuda.empty_cache()
+
+    # ---- other configurations of BASELINE.json through the same pass (rank 0)
+    if rank == 0 and not args.no_extras:
+        def rec(wd, T_, model=0, counts=0.0, steps=5):
+            r, ksec, nl = grad_rate(pt, wd, T_, steps, 3, model=model, counts=counts)
+            return {"value": r, "unit": "patterns/s", "fp32_frac": algorithmic_flops(wd, T_) / ksec / 1e12 / FP32_NOMINAL_TFLOPS,
+                    "hbm_gbs": algorithmic_bytes(wd, T_) / ksec / 1e9, "launches_per_step": nl}
+        extras = {}
+        if args.workload != "c2":
+            w2 = make_angles("c2", 0, 8)
+            extras["c2"] = rec(w2, 8, steps=10)
+            extras["c2"]["config"] = make_config("c2", 1)["workload"]
+            d2 = None
+            with pt.CGPtychoSolver(1024, 128, 128, 1, 512, 512) as s2:
+                p2, sc2, pr2 = (torch.from_numpy(w2[k][:1]).to(dev) for k in ("psi", "scan", "probe"))
+                d2 = synth_data(s2, p2, sc2, pr2)
+            extras["c2"]["cg"] = cg_rates(pt, w2, d2, torch.ones_like(p2), sc2, pr2)
+            del d2
+        c3 = workloads.c3_modes(5, 1100)
+        c3["probe"] = c3["probe_init"]
+        extras["c3_5modes"] = rec(c3, 1, steps=10)
+        extras["c3_5modes"]["config"] = "C3: 1 angle x 1100 positions, 276x600 object, 128x128 detector, 5 modes"
+        sweep = {}
+        for nd in (64, 128, 256, 512):
+            sweep[str(nd)] = rec(workloads.c5_sweep(nd, ntheta=2), 2, model=1, counts=100.0)
+        extras["c5_poisson_sweep"] = {"config": "C5: 2 angles x 1024 positions, object (4 N)^2, N^2 detector, "
+                                                "Poisson counts (mean 100), sub-pixel positions", "by_detector": sweep}
+        extra["workloads"] = extras
     if world > 1:
         barrier(world)
     if rank != 0:
         return None
+    pipe_bytes = npat * N * N * 8 * (8 + 4 + 2 + 3.1)   # DESIGN.md section 3: bytes through the L1/shared pipe
+    pipe_peak = 148 * 128 * 1.965e9
+    traffic, traffic_src = None, None
+    tpath = os.path.join(ROOT, "profiles", "traffic.json")
+    if os.path.exists(tpath):
+        try:
+            tj = json.load(open(tpath))
+            per_pattern = tj.get(args.workload + "_bytes_per_pattern")
+            if per_pattern:
+                traffic, traffic_src = per_pattern * npat, tj.get("source")
+        except Exception:
+            pass
     out = {
         "metric": "diffraction patterns/s (fwd+adj)", "value": value, "unit": "patterns/s",
         "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
-        "ms_per_step": secs / args.steps * 1e3, "higher_is_better": True, "scaling": "weak",
+        "ms_per_step": secs / args.steps * 1e3, "higher_is_better": True,
+        "scaling": "strong" if args.workload == "c4" else "weak",
         "vs_baseline": None, "dtype": "f32 (complex64)", "data": "synthetic (seeded, workloads.py)",
-        "config": {"workload": label, "patterns_per_step_per_gpu": npat,
-                   "l2": "inputs (%.0f MB measured data per step) exceed the 126 MB L2; no flush" %
-                         (data.numel() * 4 / 1e6),
-                   "parallelism": "angle shards, no collective" if world > 1 else "single GPU"},
+        "config": make_config(args.workload, world),
         "clocks": clocks,
-        "e2e": {"value": world * npat * args.steps / e2e_secs, "unit": "patterns/s",
-                "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
-                "api": "CGPtychoSolver.grad_ptycho_batch (pinned host arrays, ptheta=1 chunks)"},
+        "e2e": {"value": e2e["pinned"], "unit": "patterns/s", "h2d_bytes_per_step": h2d,
+                "d2h_bytes_per_step": d2h, "pageable": e2e["pageable"],
+                "api": "CGPtychoSolver.grad_ptycho_batch (host arrays in, host gradient out, ptheta=1 chunks)",
+                "sample": "%d angles per GPU per step (value: pinned host arrays; pageable: plain NumPy)" % E},
+        "e2e_cg": e2e_cg,
         "gpu_launches": int(launches),
-        "roofline": {"bound": "hbm", "achieved": abytes / kavg / 1e9, "peak": hbm, "unit": "GB/s",
-                     "frac": abytes / kavg / 1e9 / hbm, "traffic": None, "peak_source": peak_src,
-                     "kernel": "k_grad<gaussian, object>", "launch_ms": kavg * 1e3,
+        "roofline": {"bound": "fp32", "achieved": aflops / kavg / 1e12, "peak": FP32_NOMINAL_TFLOPS,
+                     "unit": "TFLOP/s", "frac": aflops / kavg / 1e12 / FP32_NOMINAL_TFLOPS,
+                     "traffic": traffic, "traffic_source": traffic_src,
+                     "peak_source": "nominal 148 SM x 128 lanes x 2 x 1.965 GHz (SURVEY.md 8d; "
+                                    "MEASURED_PEAKS.json carries no FP32 figure)",
+                     "kernel": "k_grad<Plan<%d>, gaussian, object>" % int(np.log2(N)),
+                     "launch_ms": kavg * 1e3, "algorithmic_flops_per_launch": aflops,
                      "algorithmic_bytes_per_launch": abytes,
-                     "fp32": {"achieved_tflops": aflops / kavg / 1e12,
-                              "peak_tflops": FP32_NOMINAL_TFLOPS,
-                              "frac": aflops / kavg / 1e12 / FP32_NOMINAL_TFLOPS,
-                              "note": "nominal peak 148 SM x 128 lanes x 2 x 1.965 GHz, FFT flops "
-                                      "20 N^2 log2 N (SURVEY.md 8d)"},
-                     "sm_data_pipe": pipe},
+                     "hbm": {"achieved_gbs": abytes / kavg / 1e9, "peak_gbs": hbm,
+                             "frac": abytes / kavg / 1e9 / hbm, "peak_source": peak_src},
+                     "sm_data_pipe": {"achieved_tbs": pipe_bytes / kavg / 1e12, "peak_tbs": pipe_peak / 1e12,
+                                      "frac": pipe_bytes / kavg / pipe_peak,
+                                      "note": "L1/shared data pipe, 128 B/clk/SM x 148 SMs x 1.965 GHz"}},
     }
-    traffic = os.path.join(ROOT, "profiles", "traffic.json")
-    if os.path.exists(traffic):
-        try:
-            out["roofline"]["traffic"] = json.load(open(traffic)).get(args.workload)
-        except Exception:
-            pass
+    out.update(extra)
     if world == 1:
         v, sample = cpu_port_rate(w)
         out["cpu_baseline"] = {"value": v, "unit": "patterns/s", "cores": os.cpu_count(),
@@ -348,108 +580,128 @@ def run_b200(args, world, rank, local):
     return out
 
 
+# ---------------------------------------------------------------------------------------------
+# the reference arm
+# ---------------------------------------------------------------------------------------------
 def run_reference(args, world, rank, local):
     """The reference's compiled cuFFT path (oracle/_ref) for the same pass; rank 0 only."""
     if rank != 0:
         return None
     from oracle import ref_gpu
-    T = args.angles
-    w, label = make_workload(args.workload, T)
+    T = REF_ANGLES if args.workload == "c4" else 8
+    w = make_angles(args.workload, 0, T)
     S, N, nz, n = w["nscan"], w["ndet"], w["nz"], w["n"]
     base = {"impl": "reference", "metric": "diffraction patterns/s (fwd+adj)", "unit": "patterns/s",
             "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "higher_is_better": True,
-            "scaling": "weak", "vs_baseline": None, "dtype": "f32 (complex64)",
-            "data": "synthetic (seeded, workloads.py)"}
+            "scaling": "strong" if args.workload == "c4" else "weak", "vs_baseline": None,
+            "dtype": "f32 (complex64)", "data": "synthetic (seeded, workloads.py)",
+            "config": make_config(args.workload, world)}
     if not (ref_gpu.available() and torch.cuda.is_available()):
         v, sample = cpu_port_rate(w, 20.0)
         base.update({"value": v, "ms_per_step": None,
-                     "config": {"workload": label, "note": "oracle/_ref absent: NumPy port on host cores"},
+                     "notes": "oracle/_ref absent: NumPy port on host cores",
                      "cpu_baseline": {"value": v, "unit": "patterns/s", "cores": os.cpu_count(),
                                       "kind": "port", "sample": sample},
                      "e2e": {"value": v, "unit": "patterns/s", "h2d_bytes_per_step": 0,
                              "d2h_bytes_per_step": 0}})
         return base
     torch.cuda.set_device(0)
-    # the reference processes one angle per call through its host helpers (ptycho.py:70-78, 143-158)
-    hdata = None
-    with ref_gpu.RefPtychoFFT(S, w["nprb"], N, 1, nz, n) as ref:
-        prb_h = np.ascontiguousarray(w["probe"][:, 0])
-        hdata = np.stack([np.abs(ref.fwd_ptycho_batch(w["psi"][t:t + 1], w["scan"][t:t + 1],
-                                                      prb_h[t:t + 1])[0]) ** 2 for t in range(T)])
-        psi_h = np.ones_like(w["psi"])
-        dev = [(torch.from_numpy(psi_h[t:t + 1]).cuda(), torch.from_numpy(w["scan"][t:t + 1]).cuda(),
-                torch.from_numpy(prb_h[t:t + 1]).cuda(), torch.from_numpy(hdata[t:t + 1]).cuda())
-               for t in range(T)]
+    prb_h = np.ascontiguousarray(w["probe"][:, 0])
+    with ref_gpu.RefPtychoFFT(S, w["nprb"], N, T, nz, n) as ref:   # one call = all T angles
+        psi_t, scan_d, prb_d = (torch.from_numpy(x).cuda() for x in (w["psi"], w["scan"], prb_h))
+        data_d = (torch.abs(ref.fwd(psi_t, scan_d, prb_d)) ** 2).contiguous()
+        psi_d = torch.ones_like(psi_t)
 
         def grad_dev(psi, scan, prb, data):
             f = ref.fwd(psi, scan, prb)                                   # ptycho.py:351 (b/a = 1)
             r = f - torch.sqrt(data) * f / (torch.sqrt(torch.abs(f) ** 2) + 1e-32)   # ptycho.py:353-354
             return ref.adj(r, scan, prb)                                  # ptycho.py:352-356
 
-        def step():
-            for a in dev:
-                grad_dev(*a)
-
-        secs, _ = timed_steps(step, args.steps, args.warmup, 1)
+        secs = timed_steps(lambda: grad_dev(psi_d, scan_d, prb_d, data_d), args.steps, args.warmup, 1)
         value = T * S * args.steps / secs
+        hdata = data_d.cpu().numpy()
+        del data_d
+    psi_h = np.ones_like(w["psi"])
+    e2e = {}
+    nrep = max(2, args.steps // 4)
+    with ref_gpu.RefPtychoFFT(S, w["nprb"], N, 1, nz, n) as ref1:
+        # the reference's host helpers process one angle per call (ptycho.py:70-78, 143-158):
+        # H2D (cp.array), operators, blocking D2H (.get()) per angle
+        def grad1(psi, scan, prb, data):
+            f = ref1.fwd(psi, scan, prb)
+            r = f - torch.sqrt(data) * f / (torch.sqrt(torch.abs(f) ** 2) + 1e-32)
+            return ref1.adj(r, scan, prb)
+        for kind in ("pinned", "pageable"):
+            src = [(pinned(x) if kind == "pinned" else x) for x in (psi_h, w["scan"], prb_h, hdata)]
 
-        def e2e_step():  # H2D from pageable numpy (cp.array) and a blocking D2H (.get()) per angle
-            out = np.empty_like(psi_h)
-            for t in range(T):
-                a = [torch.from_numpy(np.ascontiguousarray(x[t:t + 1])).cuda()
-                     for x in (psi_h, w["scan"], prb_h, hdata)]
-                out[t] = grad_dev(*a).cpu().numpy()[0]
-            return out
-        e2e_step()
+            def e2e_step():
+                out = np.empty_like(psi_h)
+                for t in range(T):
+                    a = [torch.from_numpy(np.ascontiguousarray(x[t:t + 1])).cuda() for x in src]
+                    out[t] = grad1(*a).cpu().numpy()[0]
+                return out
+            e2e_step()
+            torch.cuda.synchronize()
+            t0 = time.perf_counter()
+            for _ in range(nrep):
+                e2e_step()
+            torch.cuda.synchronize()
+            e2e[kind] = T * S * nrep / (time.perf_counter() - t0)
+            del src
+    C = min(T, CG_ANGLES)
+    with ref_gpu.RefCGPtychoSolver(S, w["nprb"], N, 1, nz, n) as r1, quiet():
+        r1.position_correction = True   # unconditional in the reference (ptycho.py:398-403)
+        r1.run_batch(hdata[:1], psi_h[:1], w["scan"][:1], w["probe"][:1], piter=2, recover_prb=True,
+                     verbose=False)
         torch.cuda.synchronize()
         t0 = time.perf_counter()
-        for _ in range(args.steps):
-            e2e_step()
+        r1.run_batch(hdata[:C], psi_h[:C], w["scan"][:C], w["probe"][:C], piter=CG_ITERS,
+                     recover_prb=True, verbose=False)
         torch.cuda.synchronize()
-        e2e_secs = time.perf_counter() - t0
-    e2e = T * S * args.steps / e2e_secs
+        e2e_cg = C * CG_ITERS / (time.perf_counter() - t0)
     cg = None
     if not args.no_cg:  # the reference's solver (cp -> torch restatement over its own operators)
-        import contextlib
-        import io
-        with ref_gpu.RefCGPtychoSolver(S, w["nprb"], N, 1, nz, n) as r1:
-            a = dev[0]
+        with ref_gpu.RefCGPtychoSolver(S, w["nprb"], N, 1, nz, n) as r1, quiet():
+            a = [torch.from_numpy(x[:1]).cuda() for x in (hdata, psi_h, w["scan"], w["probe"])]
             cg = {"iters": 6, "recover_prb": True,
                   "config": "one %s angle, device resident" % args.workload}
             for key, on in (("iters_per_s", True), ("iters_per_s_no_position_correction", False)):
                 r1.position_correction = on
-                with contextlib.redirect_stdout(io.StringIO()):
-                    r1.run(a[3], a[0], a[1].clone(), a[2][:, None].clone(), piter=2, recover_prb=True)
-                    torch.cuda.synchronize()
-                    t0 = time.perf_counter()
-                    r1.run(a[3], a[0], a[1].clone(), a[2][:, None].clone(), piter=6, recover_prb=True)
-                    torch.cuda.synchronize()
-                    cg[key] = 6 / (time.perf_counter() - t0)
+                r1.run(a[0], a[1], a[2].clone(), a[3].clone(), piter=2, recover_prb=True, verbose=False)
+                torch.cuda.synchronize()
+                t0 = time.perf_counter()
+                r1.run(a[0], a[1], a[2].clone(), a[3].clone(), piter=6, recover_prb=True, verbose=False)
+                torch.cuda.synchronize()
+                cg[key] = 6 / (time.perf_counter() - t0)
     if cg:
         base["cg"] = cg
-    base.update({"value": value, "ms_per_step": secs / args.steps * 1e3,
-                 "config": {"workload": label, "patterns_per_step_per_gpu": T * S,
-                            "note": "reference CUDA/cuFFT operators compiled unmodified (oracle/_ref) + "
-                                    "torch elementwise standing in for CuPy; GPU 0 only"},
-                 "cpu_baseline": {"value": e2e, "unit": "patterns/s", "cores": 1, "kind": "reference",
-                                  "sample": "the reference has no CPU path: its cuFFT path on one B200, "
-                                            "%d steps of %d patterns, host buffers" % (args.steps, T * S)},
-                 "e2e": {"value": e2e, "unit": "patterns/s",
+    sample = ("the reference has no CPU path: its CUDA/cuFFT operators compiled unmodified (oracle/_ref) + "
+              "torch elementwise standing in for CuPy, on ONE B200; each step = %d angles (%d patterns) "
+              "of the batch in one ptheta = %d call" % (T, T * S, T))
+    base.update({"value": value, "ms_per_step": secs / args.steps * 1e3, "notes": sample,
+                 "cpu_baseline": {"value": value, "unit": "patterns/s", "cores": 1, "kind": "reference",
+                                  "sample": sample},
+                 "e2e": {"value": e2e["pinned"], "unit": "patterns/s", "pageable": e2e["pageable"],
                          "h2d_bytes_per_step": int(hdata.nbytes + psi_h.nbytes + w["scan"].nbytes + prb_h.nbytes),
-                         "d2h_bytes_per_step": int(psi_h.nbytes)}})
+                         "d2h_bytes_per_step": int(psi_h.nbytes),
+                         "api": "per angle: H2D of the inputs, fwd -> residual -> adj, blocking D2H "
+                                "(the reference's _batch helper, ptycho.py:70-78)"},
+                 "e2e_cg": {"value": e2e_cg, "unit": "angle-iterations/s",
+                            "api": "CGPtychoSolver.run_batch(piter=%d, recover_prb=True) restated over the "
+                                   "reference's operators, pageable host arrays" % CG_ITERS,
+                            "sample": "%d angles" % C}})
     return base
 
 
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--steps", type=int, default=10)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
-    ap.add_argument("--workload", default="c2", choices=["c2", "c4"])
-    ap.add_argument("--angles", type=int, default=0,
-                    help="angles per GPU per step (default: 8 for c2, 2 for c4 = 512 MiB of data)")
+    ap.add_argument("--workload", default="c4", choices=["c2", "c4"])
     ap.add_argument("--no-cg", action="store_true")
+    ap.add_argument("--no-extras", action="store_true", help="skip the c2 / C3 / C5 sub-records")
     args = ap.parse_args()
     # stdout carries exactly ONE JSON line: anything libraries print on fd 1 meanwhile (NCCL's version
     # banner, the solver's CSV header) goes to stderr instead
@@ -457,8 +709,6 @@ def main():
     json_fd = os.dup(1)
     os.dup2(2, 1)
     args.warmup = max(args.warmup, 3)
-    if args.angles <= 0:
-        args.angles = 8 if args.workload == "c2" else 2
     if args.impl == "reference":
         rank = int(os.environ.get("RANK", "0"))
         world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -467,6 +717,8 @@ def main():
         if not torch.cuda.is_available():
             raise SystemExit("bench.py needs a B200: there is no CPU fallback for the product path")
         world, rank, local = dist_setup(args.gpus)
+        if args.workload == "c4" and C4_ANGLES % world:
+            raise SystemExit("c4 shards 168 angles evenly: use 1, 2, 4 or 8 GPUs")
         out = run_b200(args, world, rank, local)
         if world > 1:
             import torch.distributed as dist

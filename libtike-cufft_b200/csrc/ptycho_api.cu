@@ -186,8 +186,14 @@ struct ptx_plan {
   bool freed;
   int device, num_sms, grid;
   float2* tw;
-  float2* scratch;
-  size_t scratch_per_cta;  // float2
+  // per-CTA scratch, one contiguous [grid][...] array per kind; stash and accp are allocated the
+  // first time a kernel that uses them is launched (ensure_scratch)
+  float2* frame;
+  float2* stash;
+  float* accp;
+  double* slots;
+  size_t l2_window;  // bytes of `frame` covered by the persisting-L2 access-policy window (0: none)
+  float l2_hit;      // hit ratio of that window (set-aside / window)
   Geo geo;
   // position correction (lazy): tables of the last upsampling factor
   double2* reg_E;
@@ -226,9 +232,38 @@ static int plan_init(ptx_plan* p) {
   p->grid = p->num_sms * per_sm;
   const size_t npat = p->ptheta * p->nscan;
   if ((size_t)p->grid > npat) p->grid = (int)npat;
-  // per-CTA scratch: [frame (N > 128) | stash / probe accumulators | p1,p2,p3 accumulators]
-  p->scratch_per_cta = ops->scratch_per_cta;
-  CUDA_TRY(cudaMalloc(&p->scratch, p->scratch_per_cta * p->grid * sizeof(float2)));
+  CUDA_TRY(cudaMalloc(&p->slots, ops->slots_per_cta * p->grid * sizeof(double)));
+  if (ops->frame_per_cta) {
+    // N > 128: the per-CTA staging frames (8 N^2 bytes each) are written and read back twice per
+    // pattern.  They are one contiguous array so that a persisting-L2 access-policy window can pin
+    // them next to the streaming measured data (256^2: 148 x 512 KB = 76 MB of the 126 MB L2);
+    // without it ncu showed 4x the algorithmic DRAM traffic (profiles/r01l_bench_grad_c4_ncu.txt).
+    const size_t bytes = ops->frame_per_cta * p->grid * sizeof(float2);
+    CUDA_TRY(cudaMalloc(&p->frame, bytes));
+    const char* e = getenv("PTX_L2_PERSIST");
+    if (!(e && !strcmp(e, "0"))) {
+      int max_persist = 0, max_window = 0;
+      cudaDeviceGetAttribute(&max_persist, cudaDevAttrMaxPersistingL2CacheSize, p->device);
+      cudaDeviceGetAttribute(&max_window, cudaDevAttrMaxAccessPolicyWindowSize, p->device);
+      size_t want = bytes < (size_t)max_persist ? bytes : (size_t)max_persist, cur = 0;
+      cudaDeviceGetLimit(&cur, cudaLimitPersistingL2CacheSize);
+      if (want > cur && cudaDeviceSetLimit(cudaLimitPersistingL2CacheSize, want) == cudaSuccess) cur = want;
+      cudaGetLastError();
+      p->l2_window = bytes < (size_t)max_window ? bytes : (size_t)max_window;
+      p->l2_hit = p->l2_window ? (float)((double)cur / (double)p->l2_window) : 0.f;
+      if (p->l2_hit > 1.f) p->l2_hit = 1.f;
+      if (cur == 0) p->l2_window = 0;
+    }
+  }
+  return PTX_OK;
+}
+
+// stash / accp arrays on first use (a registration-only or operators-only plan never pays for them)
+static int ensure_scratch(ptx_plan* p, bool stash, bool accp) {
+  if (stash && !p->stash)
+    CUDA_TRY(cudaMalloc(&p->stash, p->ops->stash_per_cta * p->grid * sizeof(float2)));
+  if (accp && !p->accp)
+    CUDA_TRY(cudaMalloc(&p->accp, p->ops->accp_per_cta * p->grid * sizeof(float)));
   return PTX_OK;
 }
 
@@ -298,9 +333,36 @@ static int launch(ptx_plan* p, int kid, PassArgs& a, cudaStream_t st) {
   void* params[] = {&a, &tm_a, &tm_b};
   const bool nodata = kid == K_FWD || kid == K_NEAR || kid == K_ADJ_OBJ || kid == K_ADJ_PRB;
   const bool reg = kid == K_REG_OBJ || kid == K_REG_FOURIER || kid == K_REG_REAL;
-  cudaError_t e = cudaLaunchKernel(ops->kernels[kid], dim3(grid), dim3(ops->NT), params,
-                                   reg ? ops->smem_bytes_reg
-                                       : nodata ? ops->smem_bytes_nodata : ops->smem_bytes, st);
+  // scratch kinds this launch touches
+  const bool grad_prb = kid == K_GRAD_GAUSS_PRB || kid == K_GRAD_POIS_PRB || kid == K_GRADC_GAUSS_PRB ||
+                        kid == K_GRADC_POIS_PRB;
+  const bool need_stash = kid == K_ADJ_PRB || grad_prb || (ls && !a.far_in) || kid == K_REG_OBJ ||
+                          kid == K_REG_REAL;
+  const bool need_accp = reg || (inten && a.nmodes > 1) || (ls && a.npairs > 1);
+  int rc = ensure_scratch(p, need_stash, need_accp);
+  if (rc) return rc;
+  a.frame = p->frame;
+  a.slots = p->slots;
+  a.stash = need_stash ? p->stash : nullptr;
+  a.accp = need_accp ? p->accp : nullptr;
+  cudaLaunchConfig_t cfg;
+  memset(&cfg, 0, sizeof(cfg));
+  cfg.gridDim = dim3(grid);
+  cfg.blockDim = dim3(ops->NT);
+  cfg.dynamicSmemBytes = reg ? ops->smem_bytes_reg : nodata ? ops->smem_bytes_nodata : ops->smem_bytes;
+  cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  if (p->l2_window) {  // keep the staging frames in the persisting part of L2; everything else streams
+    attr[0].id = cudaLaunchAttributeAccessPolicyWindow;
+    attr[0].val.accessPolicyWindow.base_ptr = p->frame;
+    attr[0].val.accessPolicyWindow.num_bytes = p->l2_window;
+    attr[0].val.accessPolicyWindow.hitRatio = p->l2_hit;
+    attr[0].val.accessPolicyWindow.hitProp = cudaAccessPropertyPersisting;
+    attr[0].val.accessPolicyWindow.missProp = cudaAccessPropertyStreaming;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+  }
+  cudaError_t e = cudaLaunchKernelExC(&cfg, ops->kernels[kid], params);
   g_launches.fetch_add(1);
   if (e != cudaSuccess) return fail(PTX_ECUDA, "launch %s: %s", ops->names[kid], cudaGetErrorString(e));
   CUDA_TRY(cudaGetLastError());
@@ -323,8 +385,6 @@ static PassArgs base_args(const ptx_plan* p) {
   memset(&a, 0, sizeof(a));
   a.g = p->geo;
   a.tw = p->tw;
-  a.scratch = p->scratch;
-  a.scratch_per_cta = p->scratch_per_cta;
   return a;
 }
 
@@ -368,7 +428,12 @@ int ptx_create(ptx_plan** out, size_t ptheta, size_t nz, size_t n, size_t nscan,
   p->ops = ops_for(L);
   p->freed = false;
   p->tw = nullptr;
-  p->scratch = nullptr;
+  p->frame = nullptr;
+  p->stash = nullptr;
+  p->accp = nullptr;
+  p->slots = nullptr;
+  p->l2_window = 0;
+  p->l2_hit = 0.f;
   p->reg_E = nullptr;
   p->reg_AT = nullptr;
   p->reg_uf = 0;
@@ -390,7 +455,8 @@ int ptx_create(ptx_plan** out, size_t ptheta, size_t nz, size_t n, size_t nscan,
   int rc = plan_init(p);
   if (rc) {
     if (p->tw) cudaFree(p->tw);
-    if (p->scratch) cudaFree(p->scratch);
+    if (p->frame) cudaFree(p->frame);
+    if (p->slots) cudaFree(p->slots);
     delete p;
     return rc;
   }
@@ -402,14 +468,20 @@ int ptx_free(ptx_plan* p) {
   if (!p) return fail(PTX_EINVAL, "null plan");
   if (!p->freed) {
     cudaFree(p->tw);
-    cudaFree(p->scratch);
+    if (p->frame) cudaFree(p->frame);
+    if (p->stash) cudaFree(p->stash);
+    if (p->accp) cudaFree(p->accp);
+    if (p->slots) cudaFree(p->slots);
     if (p->reg_E) cudaFree(p->reg_E);
     if (p->reg_AT) cudaFree(p->reg_AT);
     p->tw = nullptr;
-    p->scratch = nullptr;
+    p->frame = nullptr;
+    p->stash = nullptr;
+    p->accp = nullptr;
+    p->slots = nullptr;
     p->reg_E = nullptr;
     p->reg_AT = nullptr;
-      p->freed = true;
+    p->freed = true;
   }
   return PTX_OK;
 }
@@ -721,7 +793,14 @@ int ptx_prepare_data(const float* raw, const long long* ids, size_t nsel, size_t
   if (((uintptr_t)raw | (uintptr_t)out) & 15) return fail(PTX_EINVAL, "ptx_prepare_data: arrays must be 16-byte aligned");
   const size_t total = nsel * n * (n / 4);
   size_t b = (total + 255) / 256;
-  const int grid = (int)(b > 148 * 16 ? 148 * 16 : b);
+  static const size_t cap = []() {
+    int dev = 0, sms = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess ||
+        cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || sms < 1)
+      sms = 148;
+    return (size_t)sms * 16;
+  }();
+  const int grid = (int)(b > cap ? cap : b);
   k_prepare_data<<<grid, 256, 0, (cudaStream_t)stream>>>(raw, ids, nsel, (int)n, denominator, fftshift, out);
   g_launches.fetch_add(1);
   CUDA_TRY(cudaGetLastError());

@@ -47,8 +47,12 @@ __device__ __forceinline__ Pat make_pat(const float2* __restrict__ scan, int idx
   p.rho = sc.x - rI;
   p.gam = sc.y - cI;
   p.skip = (rI < 0.f) || (cI < 0.f);  // -0.0 is not < 0: (-1,0) is NOT skipped, as in the reference
-  p.R = (int)rI;
-  p.C = (int)cI;
+  // a window that starts at or beyond the object's last row / column (or a NaN / inf position, for
+  // which the int conversion below would saturate and the bounds arithmetic overflow) only sees the
+  // zero extension of Q11: far field 0, no adjoint contribution -- the same thing as a skip
+  p.skip = p.skip || !(rI < (float)g.nz) || !(cI < (float)g.n);
+  p.R = p.skip ? 0 : (int)rI;
+  p.C = p.skip ? 0 : (int)cI;
   p.w00 = (1.f - p.gam) * (1.f - p.rho);
   p.w01 = p.gam * (1.f - p.rho);
   p.w10 = (1.f - p.gam) * p.rho;

@@ -20,8 +20,12 @@ constexpr int REG_JROWS = 160;  // rows of the Chebyshev table T[j][n] (zero bey
 struct PassArgs {
   Geo g;
   const float2* tw;        // twiddle tables (global, copied to smem by every CTA)
-  float2* scratch;         // per-CTA scratch (L2 resident): [frame | stash | accp]
-  size_t scratch_per_cta;  // in float2
+  // per-CTA global scratch, one CONTIGUOUS array per kind ([grid][...]; a CTA's slice is indexed by
+  // blockIdx.x).  A plan may therefore only be used from one stream at a time.
+  float2* frame;           // [grid][N*N]   staging frame of the N > 128 plans (kept L2-resident)
+  float2* stash;           // [grid][N*N]   parked far field / probe accumulators (allocated on first use)
+  float* accp;             // [grid][3*N*N] intensity / p1,p2,p3 accumulators, registration product
+  double* slots;           // [grid][16*NT] thread-private running sums
   const float2* psi;       // [T,nz,n]
   const float2* psi_b;     // second object (line search)
   const float2* prb;       // probe base of the mode to use, angle stride prb_ts
@@ -65,7 +69,9 @@ struct PlanOps {
   size_t smem_bytes;       // dynamic shared memory of the kernels that read measured data
   size_t smem_bytes_nodata;  // ... of the others (no data tile: more of the SM's SRAM stays L1)
   size_t smem_bytes_reg;     // ... of the position-correction kernels
-  size_t scratch_per_cta;  // float2
+  size_t frame_per_cta, stash_per_cta;  // float2 (frame: 0 for single-tile plans)
+  size_t accp_per_cta;     // floats
+  size_t slots_per_cta;    // doubles
   int tw_total;            // float2
   void (*fill_tw)(float2*);
   int patch_w, patch_h;    // TMA box of the object patch in complex elements (0: no TMA gather)

@@ -30,12 +30,11 @@ struct Smem {
 };
 
 template <class P>
-struct Scratch {  // per-CTA global scratch, in float2
-  static constexpr size_t FRAME = P::RC > 1 ? (size_t)P::N * P::N : 0;
-  static constexpr size_t STASH = (size_t)P::N * P::N;
-  static constexpr size_t ACCP = (size_t)3 * P::N * P::N / 2;
-  static constexpr size_t SLOTS = (size_t)16 * P::NT;  // doubles = float2-sized
-  static constexpr size_t TOTAL = FRAME + STASH + ACCP + SLOTS;
+struct Scratch {  // per-CTA global scratch; every kind is its own contiguous [grid][...] array
+  static constexpr size_t FRAME = P::RC > 1 ? (size_t)P::N * P::N : 0;  // float2
+  static constexpr size_t STASH = (size_t)P::N * P::N;                  // float2
+  static constexpr size_t ACCP = (size_t)3 * P::N * P::N;               // floats
+  static constexpr size_t SLOTS = (size_t)16 * P::NT;                   // doubles
 };
 
 template <class P>
@@ -48,13 +47,15 @@ __device__ __forceinline__ void cta_setup(Cta<P>& c, unsigned char* raw, const P
   c.bar = reinterpret_cast<unsigned long long*>(raw + Smem<P>::OFF_BAR);
   for (int i = c.tid; i < Smem<P>::TW; i += P::NT) tw[i] = a.tw[i];
   c.tw = tw;
-  float2* scr = a.scratch + (size_t)blockIdx.x * a.scratch_per_cta;
-  c.frame = scr;
-  c.stash = scr + Scratch<P>::FRAME;
-  c.accp = reinterpret_cast<float*>(c.stash + Scratch<P>::STASH);
-  c.slots = reinterpret_cast<double*>(c.stash + Scratch<P>::STASH + Scratch<P>::ACCP) + c.tid;
+  // kernels are only handed the scratch kinds they use (ptycho_api.cu: launch()); the others are null
+  c.frame = a.frame + (size_t)blockIdx.x * Scratch<P>::FRAME;
+  c.stash = a.stash + (size_t)blockIdx.x * Scratch<P>::STASH;
+  c.accp = a.accp + (size_t)blockIdx.x * Scratch<P>::ACCP;
+  c.slots = a.slots + (size_t)blockIdx.x * Scratch<P>::SLOTS + c.tid;
+  if (a.slots) {
 #pragma unroll
-  for (int k = 0; k < 16; ++k) c.slots[k * P::NT] = 0.0;
+    for (int k = 0; k < 16; ++k) c.slots[k * P::NT] = 0.0;
+  }
   fixed_coords<typename P::S0, P::WBITS>(c.tid, c.xf0, c.yf0);
   fixed_coords<typename P::S2, P::WBITS>(c.tid, c.xf2, c.yf2);
   c.sbase = spec_base<P>(c.xf2, c.yf2);
@@ -63,30 +64,65 @@ __device__ __forceinline__ void cta_setup(Cta<P>& c, unsigned char* raw, const P
   __syncthreads();
 }
 
-// Square roots / reciprocals through the SFU (MUFU.RSQ / MUFU.RCP, <= 2 ulp) instead of the IEEE
-// slow-path subroutines: a handful of instructions per pixel, and a relative error (2.4e-7) far
-// below the 1e-5 operator bar.  Arguments are clamped at 1e-35 so that exact zeros stay finite.
+// PTX_MATH selects how the per-pixel square roots, reciprocals and logarithms of the residual and of
+// the cost are evaluated:
+//   0 (default)  SFU approximations (MUFU.RSQ / MUFU.RCP, <= 2 ulp, relative error 2.4e-7 -- far below
+//                the 1e-5 operator bar): a handful of instructions per pixel (logf is CUDA's 1-ulp one);
+//   1            IEEE-rounded sqrtf / division and the reference's literal expression order
+//                (ptycho.py:353, 360, 308-314).  Built as a second library by `__graft_entry__.build(
+//                variants=True)` for the CG-parity A/B of tests/tools/cg_parity_probe.py.
+#ifndef PTX_MATH
+#define PTX_MATH 0
+#endif
+
 __device__ __forceinline__ float frsq(float x) {
+#if PTX_MATH == 1
+  return 1.0f / sqrtf(fmaxf(x, 1e-35f));
+#else
   float r;
   asm("rsqrt.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(fmaxf(x, 1e-35f)));
   return r;
+#endif
 }
-__device__ __forceinline__ float fsqrt(float x) { return x * frsq(x); }  // 0 -> 0
+__device__ __forceinline__ float fsqrt(float x) {  // 0 -> 0
+#if PTX_MATH == 1
+  return sqrtf(x);
+#else
+  return x * frsq(x);
+#endif
+}
 __device__ __forceinline__ float frcp(float x) {
+#if PTX_MATH == 1
+  return 1.0f / x;
+#else
   float r;
   asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
   return r;
+#endif
 }
 
 // residual factor of one far-field pixel (ptycho.py:353, 360): the residual is F * factor
 //   gaussian: fscale * (1 - sqrt(d) / (sqrt(I) + 1e-32)) = fscale - fscale * d * rsqrt(d * I)
 //   poisson:  fscale * (1 - d / (I + 1e-32))
+// The one-MUFU Gaussian form needs d * I to be a normal number: products below 1e-30 (data scaled
+// far below 1 next to vanishing intensities) take the literal two-root expression instead.
 template <int MODEL>
 __device__ __forceinline__ float residual_factor(float d, float I, float fscale) {
-  if (MODEL == PTX_MODEL_GAUSSIAN)
-    return fmaf(-(fscale * d), frsq(d * I), fscale);
-  else
+  if (MODEL == PTX_MODEL_GAUSSIAN) {
+#if PTX_MATH == 1
+    return fscale - fscale * sqrtf(d) / (sqrtf(I) + 1e-32f);
+#else
+    const float q = d * I;
+    if (q < 1e-30f) return fscale - fscale * sqrtf(d) / (sqrtf(I) + 1e-32f);
+    return fmaf(-(fscale * d), frsq(q), fscale);
+#endif
+  } else {
+#if PTX_MATH == 1
+    return fscale - fscale * d / (I + 1e-32f);
+#else
     return fmaf(-(fscale * d), frcp(I + 1e-32f), fscale);
+#endif
+  }
 }
 
 // minimisation functional per pixel (ptycho.py:308-314), x = intensity estimate, d = data

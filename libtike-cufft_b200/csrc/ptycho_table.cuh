@@ -25,7 +25,10 @@ void fill_ops_base(PlanOps& ops) {
   ops.smem_bytes = Smem<P>::BYTES;
   ops.smem_bytes_nodata = Smem<P>::BYTES_NODATA;
   ops.smem_bytes_reg = RegGeom<P>::SMEM;
-  ops.scratch_per_cta = Scratch<P>::TOTAL;
+  ops.frame_per_cta = Scratch<P>::FRAME;
+  ops.stash_per_cta = Scratch<P>::STASH;
+  ops.accp_per_cta = Scratch<P>::ACCP;
+  ops.slots_per_cta = Scratch<P>::SLOTS;
   ops.tw_total = TwLayout<P>::TOTAL;
   ops.fill_tw = fill_tw_host<P>;
   ops.patch_w = Patch<P>::TMA ? Patch<P>::W : 0;

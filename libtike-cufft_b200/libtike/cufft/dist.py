@@ -105,6 +105,12 @@ class ScalarComm(object):
             self.calls += 1
         return t
 
+    def min_(self, t):
+        if self.world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MIN, group=self.group)
+            self.calls += 1
+        return t
+
     def probe_grad_(self, g):
         """Shared-probe mode: one probe for every angle -> its gradient is summed over ranks."""
         if self.shared_probe and self.world > 1:

@@ -30,13 +30,15 @@ Documented deviations from the reference (see DESIGN.md "Quirks"):
 """
 import ctypes
 import warnings
+import weakref
 
 import numpy as np
 import torch
 
 from libtike.cufft.ptychofft import ptychofft, lib, check, current_stream, PtxError  # noqa: F401
 
-__all__ = ["PtychoCuFFT", "CGPtychoSolver", "register_translation_batch", "line_search_gammas"]
+__all__ = ["PtychoCuFFT", "CGPtychoSolver", "register_translation_batch", "line_search_gammas",
+           "release_registration_plans"]
 
 MODELS = {"gaussian": 0, "poisson": 1}
 
@@ -52,6 +54,39 @@ def _dev_tensor(x, dtype=None):
 
 def _ptr(t):
     return ctypes.c_void_p(t.data_ptr())
+
+
+_HOST_REGISTERED = {}  # base address -> (nbytes, weakref.finalize)
+#: page-lock large caller-owned NumPy arrays in place the first time a host-array entry point sees
+#: them (cudaHostRegister, cached per array, released when the array is garbage collected): their
+#: chunks are then DMA'd straight from the caller's memory instead of going through a staging copy
+HOST_REGISTER_MIN_BYTES = 8 << 20
+
+
+def _host_tensor(a):
+    """CPU tensor view of (a chunk of) a caller's NumPy array, page-locked in place when possible."""
+    a = np.ascontiguousarray(a)
+    t = torch.from_numpy(a)
+    if t.is_pinned() or HOST_REGISTER_MIN_BYTES is None:
+        return t
+    base = a
+    while isinstance(base.base, np.ndarray):
+        base = base.base
+    if base.nbytes < HOST_REGISTER_MIN_BYTES or not base.flags.c_contiguous or not base.flags.writeable:
+        return t
+    ptr = base.ctypes.data
+    if ptr not in _HOST_REGISTERED or _HOST_REGISTERED[ptr][0] < base.nbytes:
+        rt = torch.cuda.cudart()
+        if ptr in _HOST_REGISTERED:
+            _HOST_REGISTERED.pop(ptr)[1]()
+        if int(rt.cudaHostRegister(ptr, base.nbytes, 0)) != 0:
+            return t  # e.g. memory that cannot be locked: stays pageable, the caller stages it
+
+        def release(p=ptr):
+            if _HOST_REGISTERED.pop(p, None) is not None:
+                torch.cuda.cudart().cudaHostUnregister(p)
+        _HOST_REGISTERED[ptr] = (base.nbytes, weakref.finalize(base, release))
+    return t
 
 
 class _TorchArrayModule(object):
@@ -165,8 +200,8 @@ class PtychoCuFFT(ptychofft):
     def _batch(self, function, output, *inputs):
         """Host <-> device shuffle, ptycho.py:70-78, chunked by ptheta (Q9).
 
-        Inputs are staged through pinned memory and copied on torch's current
-        stream; the result lands in `output` (a host array) chunk by chunk.
+        Inputs are copied (pageable, like the reference's `cp.array`) on torch's current stream;
+        the result lands in `output` (a host array) chunk by chunk.
         """
         T = self.ptheta
         ntheta = inputs[0].shape[0]
@@ -220,10 +255,14 @@ class PtychoCuFFT(ptychofft):
         def stage(k):
             ids = slice(k * T, (k + 1) * T)
             with torch.cuda.stream(copy_stream):
-                dev = [torch.from_numpy(np.ascontiguousarray(x[ids])).pin_memory().cuda(non_blocking=True)
-                       for x in (data, psi, scan, probe)]
+                dev = []
+                for x in (data, psi, scan, probe):
+                    h = _host_tensor(x[ids])
+                    dev.append((h if h.is_pinned() else h.pin_memory()).cuda(non_blocking=True))
                 ev = torch.cuda.Event()
                 ev.record(copy_stream)
+            for t in dev:  # allocated on copy_stream, consumed by kernels on `main`: keep the blocks
+                t.record_stream(main)  # out of copy_stream's pool until main is done with them
             return ids, dev, ev
 
         pending = []  # (ids, pinned psi, pinned probe, event) of results in flight
@@ -254,6 +293,13 @@ class PtychoCuFFT(ptychofft):
 _REG_PLANS = {}
 
 
+def release_registration_plans():
+    """Free the per-(detector size, device) plans `register_translation_batch` keeps between calls."""
+    for plan in _REG_PLANS.values():
+        plan.free()
+    _REG_PLANS.clear()
+
+
 def register_translation_batch(src_image, target_image, upsample_factor=1, space="real"):
     """Batched sub-pixel image registration by phase correlation (reference: ptycho.py:192-248).
 
@@ -278,7 +324,9 @@ def register_translation_batch(src_image, target_image, upsample_factor=1, space
     S, N = src.shape[0], src.shape[2]
     key = (N, src.device.index)
     plan = _REG_PLANS.get(key)
-    if plan is None:  # a plan only carries twiddles and per-CTA scratch; object size is irrelevant here
+    if plan is None:
+        # a plan carries twiddles and the per-CTA scratch its kernels touch (allocated on first use:
+        # a registration-only plan never pays for the solver's accumulators); object size is irrelevant
         plan = _REG_PLANS[key] = ptychofft(1, N + 1, N + 1, 4096, N, N)
     shifts = torch.empty((S, 2), dtype=torch.float64, device=src.device)
     check(lib.ptx_register_translation(plan._h, _ptr(src), _ptr(tgt), S,
@@ -314,9 +362,6 @@ class CGPtychoSolver(PtychoCuFFT):
     #: intensity that mode m + 1 starts from as I + g^2 p2 + g p3 (one pass over the intensity map)
     #: instead of M forward operators (ptycho.py:424-428)
     incremental_intensity = True
-    #: diagnostics hook used by the parity tests: a list of raw line-search results, consumed in call
-    #: order, that override the solver's own decisions (the costs are still evaluated and logged)
-    _forced_steps = None
     #: optional libtike.cufft.dist.ScalarComm: when set, the CG scalars (and, in shared-probe mode,
     #: the probe gradient) are all-reduced over its process group, so that ranks holding different
     #: angles behave like ONE reference run over all of them
@@ -375,7 +420,7 @@ class CGPtychoSolver(PtychoCuFFT):
         the ones evaluated in the deciding pass."""
         K = int(self.ls_candidates)
         c0 = 0
-        forced = self._forced_steps.pop(0) if self._forced_steps else None
+        self._ls_begin()
         self._ls_ab = None
 
         def done(step, c):
@@ -396,16 +441,26 @@ class CGPtychoSolver(PtychoCuFFT):
                                         _ptr(cost), current_stream()))
             c = self._sum(cost).cpu().numpy()
             self.ls_log.append((c0, c[:1 + K].copy()))
-            if forced is not None and (forced == 0 or forced >= 2.0 ** -(c0 + K - 1)):
-                return done(forced, c)
-            for j in range(K):
-                step = 2.0 ** -(c0 + j)
-                if forced is None and not (c[1 + j] > c[0]):
-                    return done(step, c)
-                if step < 1e-32:
-                    warnings.warn("Line search failed for conjugate gradient.")
-                    return done(0, c)
+            step = self._ls_decide(c0, c, K)
+            if step is not None:
+                return done(step, c)
             c0 += K
+
+    def _ls_begin(self):
+        """Called once per line search, before its first pass (a seam for instrumented subclasses)."""
+
+    def _ls_decide(self, c0, c, K):
+        """The decision line_search_sqr (ptycho.py:272-281) takes on the K candidate costs c[1:1+K] of
+        steps 2^-c0 .. 2^-(c0+K-1) against c[0] = f(p1): the accepted step, 0 when the search failed,
+        or None to keep halving."""
+        for j in range(K):
+            step = 2.0 ** -(c0 + j)
+            if not (c[1 + j] > c[0]):
+                return step
+            if step < 1e-32:
+                warnings.warn("Line search failed for conjugate gradient.")
+                return 0
+        return None
 
     def _dai_yuan(self, grad, grad0, d, first):
         red = torch.zeros(3, dtype=torch.float64, device=grad.device)
@@ -480,13 +535,14 @@ class CGPtychoSolver(PtychoCuFFT):
                 out[slot["ids"]] = slot["gh"].numpy()
                 slot["done"] = None
 
+        computed = None  # event after the kernels of the previous chunk
         for c in range(nchunk):
             slot, stream = st["slots"][c % 2], st["streams"][c % 2]
             drain(slot)  # the pinned buffers of this slot are free again
             ids = slice(c * T, (c + 1) * T)
             srcs = []
             for hbuf, src in zip(slot["h"], (data, psi, scan, probe)):
-                t = torch.from_numpy(np.ascontiguousarray(src[ids]))
+                t = _host_tensor(src[ids])
                 if not t.is_pinned():  # pageable caller memory is staged; pinned memory is DMA'd as is
                     hbuf.copy_(t)
                     t = hbuf
@@ -496,11 +552,17 @@ class CGPtychoSolver(PtychoCuFFT):
                     dbuf.copy_(t, non_blocking=True)
                 d_data, d_psi, d_scan, d_prb = slot["d"]
                 slot["g"].zero_()
+                # the plan's per-CTA scratch (staging frames, accumulators) is indexed by blockIdx
+                # only: kernels of two chunks must never overlap, only copies do
+                if computed is not None:
+                    stream.wait_event(computed)
                 if M > 1:
                     self._intensity(d_psi, d_scan, d_prb, d_data, slot["inten"], mdl)
                 for k in range(M):
                     self._grad(0, d_psi, d_scan, d_prb, k, d_data, slot["inten"], 1.0, 1.0, 1.0, mdl,
                                slot["g"], sc=st["sc"])
+                computed = torch.cuda.Event()
+                computed.record(stream)
                 slot["gh"].copy_(slot["g"], non_blocking=True)
                 slot["done"] = torch.cuda.Event()
                 slot["done"].record(stream)
@@ -526,7 +588,8 @@ class CGPtychoSolver(PtychoCuFFT):
             raise ValueError("model must be 'gaussian' or 'poisson'")
         mdl = MODELS[model]
         data = _dev_tensor(data).contiguous()
-        scan = _dev_tensor(scan).contiguous()
+        scan_in = _dev_tensor(scan)  # position correction updates the caller's array (ptycho.py:403)
+        scan = scan_in if scan_in.is_contiguous() else scan_in.contiguous()
         psi = _dev_tensor(psi).contiguous().clone()  # the reference rebinds psi (ptycho.py:405)
         probe_in = _dev_tensor(probe)
         probe = probe_in if probe_in.is_contiguous() else probe_in.contiguous()  # mutated in place (Q6)
@@ -539,11 +602,18 @@ class CGPtychoSolver(PtychoCuFFT):
         # F(psi, probe_k) of the gradient passes, re-read by the line searches that follow them
         # (both shortcuts are dropped, not shrunk, when their arrays would not fit comfortably)
         free_bytes = torch.cuda.mem_get_info(dev)[0]
+        fits = [bool(self.cache_far_field and 8 * M * data.numel() < 0.4 * free_bytes),
+                bool(multi and recover_prb and self.incremental_intensity
+                     and 8 * (M + 1) * data.numel() < 0.6 * free_bytes)]
+        if self.comm is not None:
+            # every rank must take the same shortcuts: they decide how many collectives an iteration
+            # issues (a rank that skips an intensity pass skips its all-reduce)
+            f = torch.tensor([float(x) for x in fits], dtype=torch.float64, device=dev)
+            fits = [bool(x > 0.5) for x in self.comm.min_(f).cpu().tolist()]
         far = (torch.empty((M,) + tuple(data.shape), dtype=torch.complex64, device=dev)
-               if (self.cache_far_field and 8 * M * data.numel() < 0.4 * free_bytes) else None)
+               if fits[0] else None)
         p23 = (torch.empty(tuple(data.shape) + (2,), dtype=torch.float32, device=dev)
-               if (multi and recover_prb and self.incremental_intensity
-                   and 8 * data.numel() < 0.2 * torch.cuda.mem_get_info(dev)[0]) else None)
+               if fits[1] else None)
         sum_data = float(self._sum(data.sum(dtype=torch.float64).reshape(1))) if mdl == 0 else 0.0
 
         gradpsi = torch.zeros_like(psi)
@@ -565,7 +635,7 @@ class CGPtychoSolver(PtychoCuFFT):
         reuse = bool(self.reuse_line_search_sums) and recover_prb and (M == 1 or p23 is not None)
         self.history = []  # (iteration, step size object, step size probe) -- diagnostics only
         self.ls_log = []   # (first candidate exponent, [f(0), f(2^-c0), ...]) per fused pass
-        self.ls_steps = []  # raw result of every line search, in call order (replayable: _forced_steps)
+        self.ls_steps = []  # raw result of every line search, in call order (replayable by an instrumented subclass)
         self.shift_log = []  # device [S,2] float64 shifts of every position-correction step
         for i in range(piter):
             # 1) object retrieval subproblem with fixed probes (ptycho.py:327-345).  a, b, the probe
@@ -656,4 +726,6 @@ class CGPtychoSolver(PtychoCuFFT):
 
         if probe is not probe_in:
             probe_in.copy_(probe)
+        if scan is not scan_in:
+            scan_in.copy_(scan)
         return {"psi": psi, "probe": probe_in}

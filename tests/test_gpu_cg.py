@@ -11,7 +11,7 @@ import torch
 import workloads
 from oracle import numpy_ptycho as O
 from oracle import ref_gpu
-from util import rel_l2
+from util import rel_l2, ReplaySolver
 
 pytestmark = pytest.mark.gpu
 GOLD = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
@@ -131,7 +131,7 @@ def test_cg_vs_reference_gpu(nmodes, nscan, model, piter, ndet, noisy):
 
     The line search compares cost sums whose differences can be far below the fp32 resolution of
     the reference's own reductions, so a near-tie may be decided either way and fork a long run.
-    Parity proper therefore replays the reference's decisions (`_forced_steps`): everything else
+    Parity proper therefore replays the reference's decisions (`forced_steps`): everything else
     -- gradients, directions, updates, probe rescaling -- must then agree (see _assert_parity),
     every decision is audited against my own costs, and the free-running result must agree too as
     long as no near-tie was decided differently.  Data: noise-free intensities (tests/test.py:51)
@@ -151,14 +151,14 @@ def test_cg_vs_reference_gpu(nmodes, nscan, model, piter, ndet, noisy):
             return O.cg_run(data, psi0, scan, prb0.copy(), piter, model, True,
                             forced_steps=list(steps))
 
-    with pt.CGPtychoSolver(nscan, ndet, ndet, 1, nz, n) as slv:
-        slv._forced_steps = list(steps)
+    with ReplaySolver(nscan, ndet, ndet, 1, nz, n) as slv:
+        slv.forced_steps = list(steps)
         got = slv.run_batch(data, psi0, scan, prb0, piter=piter, model=model, recover_prb=True)
         same = _assert_parity(got, want, exact,
                               "(replayed decisions) %s" % ((nmodes, nscan, model, piter, ndet),))
         mism = _audit_decisions(slv, steps, strict=same)
         print("   near ties decided differently:", mism, "of", len(steps))
-        slv._forced_steps = None
+        slv.forced_steps = None
         free = slv.run_batch(data, psi0, scan, prb0, piter=piter, model=model, recover_prb=True)
         f_psi, f_prb = rel_l2(free["psi"], got["psi"]), rel_l2(free["probe"], got["probe"])
         print("   free running vs replayed: psi %.2e probe %.2e" % (f_psi, f_prb))
@@ -195,9 +195,9 @@ def test_cg_vs_reference_gpu_position_correction(nmodes, nscan, model, piter, nd
             return O.cg_run(data, psi0, scan.copy(), prb0.copy(), piter, model, True,
                             forced_steps=list(steps), position_correction=True)
 
-    with pt.CGPtychoSolver(nscan, ndet, ndet, 1, nz, n) as slv:
+    with ReplaySolver(nscan, ndet, ndet, 1, nz, n) as slv:
         slv.position_correction = True
-        slv._forced_steps = list(steps)
+        slv.forced_steps = list(steps)
         got = slv.run_batch(data, psi0, scan, prb0, piter=piter, model=model, recover_prb=True)
         glog = [x.cpu().numpy() for x in slv.shift_log]
         assert len(glog) == len(rlog) == piter - 1
@@ -251,8 +251,8 @@ def test_cg_vs_golden(name):
             return O.cg_run(data, z["psi0"], scan, z["probe0"].copy(), int(z["piter"]),
                             str(z["model"]), True, forced_steps=list(steps))
 
-    with pt.CGPtychoSolver(nscan, ndet, ndet, 1, nz, n) as slv:
-        slv._forced_steps = list(steps)  # replay the reference's line-search decisions (see above)
+    with ReplaySolver(nscan, ndet, ndet, 1, nz, n) as slv:
+        slv.forced_steps = list(steps)  # replay the reference's line-search decisions (see above)
         got = slv.run_batch(data, z["psi0"], scan, z["probe0"], piter=int(z["piter"]),
                             model=str(z["model"]), recover_prb=True)
         same = _assert_parity(got, {"psi": z["psi"], "probe": z["probe"]}, exact, name)
@@ -309,9 +309,9 @@ def test_cg_skipped_positions_window_and_two_angles(ndet, nprb, model, poscorr):
             return O.cg_run(data, psi0, scan.copy(), prb0.copy(), piter, model, True, ndet=ndet,
                             forced_steps=list(steps), position_correction=poscorr)
 
-    with pt.CGPtychoSolver(S, nprb, ndet, T, nz, n) as slv:
+    with ReplaySolver(S, nprb, ndet, T, nz, n) as slv:
         slv.position_correction = poscorr
-        slv._forced_steps = list(steps)
+        slv.forced_steps = list(steps)
         got = slv.run_batch(data, psi0, scan, prb0, piter=piter, model=model, recover_prb=True)
         same = _assert_parity(got, want, exact, "(skips, window, ptheta=2) %s" % ((ndet, nprb, model, poscorr),))
         _audit_decisions(slv, steps, strict=same)
@@ -336,13 +336,13 @@ def test_cg_shortcuts_do_not_change_results(model, ndet):
     res = {}
     steps = None
     for fast in (False, True):
-        with pt.CGPtychoSolver(nscan, ndet, ndet, 1, nz, n) as slv:
+        with ReplaySolver(nscan, ndet, ndet, 1, nz, n) as slv:
             slv.position_correction = True
             slv.cache_far_field = fast
             slv.reuse_line_search_sums = fast
             # near-tie step decisions are noise (atomic summation order): the second run replays
             # the first one's, so that everything else must agree to rounding
-            slv._forced_steps = list(steps) if steps is not None else None
+            slv.forced_steps = list(steps) if steps is not None else None
             res[fast] = (slv.run_batch(data, psi0, scan, prb0, piter=6, model=model, recover_prb=True),
                          list(slv.history))
             steps = list(slv.ls_steps)
@@ -364,9 +364,9 @@ def test_cg_incremental_intensity_multi_mode(model, nmodes):
     res = {}
     steps = None
     for fast in (False, True):
-        with pt.CGPtychoSolver(nscan, ndet, ndet, 1, nz, n) as slv:
+        with ReplaySolver(nscan, ndet, ndet, 1, nz, n) as slv:
             slv.incremental_intensity = fast
-            slv._forced_steps = list(steps) if steps is not None else None  # replay (near ties are noise)
+            slv.forced_steps = list(steps) if steps is not None else None  # replay (near ties are noise)
             res[fast] = (slv.run_batch(data, psi0, scan, prb0, piter=5, model=model, recover_prb=True),
                          list(slv.history))
             steps = list(slv.ls_steps)

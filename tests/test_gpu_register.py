@@ -12,7 +12,7 @@ import workloads
 from oracle import numpy_ptycho as O
 from oracle import ref_gpu
 from test_register_oracle import smooth_images, fourier_shift
-from util import rel_l2
+from util import rel_l2, ReplaySolver
 
 pytestmark = pytest.mark.gpu
 
@@ -208,8 +208,8 @@ def test_c2_full_size_position_correction_vs_reference():
                              verbose=False)
         steps = [t[2] for t in ref.last_trials]
         rlog = ref.shift_log
-    with pt.CGPtychoSolver(S, 128, 128, 1, 512, 512) as slv:
-        slv._forced_steps = list(steps)
+    with ReplaySolver(S, 128, 128, 1, 512, 512) as slv:
+        slv.forced_steps = list(steps)
         got = slv.run_batch(data, init, scan, prb0, piter=3, model="gaussian", recover_prb=True)
         glog = [x.cpu().numpy() for x in slv.shift_log]
     nbad = sum(int((np.abs(a - b).max(axis=1) > 0).sum()) for a, b in zip(glog, rlog))

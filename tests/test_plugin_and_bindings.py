@@ -1,0 +1,175 @@
+"""Boundary proofs:
+
+* the `tike.PtychoBackend: cudafft` entry point of the reference (/root/reference/setup.py:27-31)
+  resolves, after a real `pip install` of libtike-cufft_b200/ into a scratch target, to this
+  package's `PtychoCuFFT`, and the resolved class runs the reference's adjoint test (C1) on the GPU;
+* INTEGRATION.md option B -- the reference's pybind11 module surface
+  (/root/reference/src/cuda/pybind11/ptychofft.cxx:8-26) over the C ABI -- is compiled by build()
+  and drives the kernels through raw device addresses exactly like the ctypes class;
+* device arrays that are not torch tensors but expose `__cuda_array_interface__` (what the
+  reference's callers hold: CuPy arrays) are accepted by the operator class.
+"""
+import json
+import os
+import subprocess
+import sys
+
+import numpy as np
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+PKG = os.path.join(ROOT, "libtike-cufft_b200")
+
+
+@pytest.fixture(scope="module")
+def installed(tmp_path_factory):
+    """`pip install` of the package (setup.py + entry point + the built .so as package data)."""
+    sys.path.insert(0, ROOT)
+    import __graft_entry__
+    __graft_entry__.build()
+    target = str(tmp_path_factory.mktemp("site"))
+    p = subprocess.run([sys.executable, "-m", "pip", "install", "--no-index", "--no-build-isolation",
+                        "--no-deps", "--quiet", "--target", target, PKG],
+                       capture_output=True, text=True, timeout=900)
+    assert p.returncode == 0, p.stdout[-2000:] + p.stderr[-2000:]
+    return target
+
+
+def _run_installed(target, code, timeout=600):
+    """Run `code` in a fresh interpreter that sees the INSTALLED package (and the repo root for
+    workloads / oracle), not the in-tree one."""
+    env = dict(os.environ, PYTHONPATH=os.pathsep.join([target, ROOT]))
+    p = subprocess.run([sys.executable, "-c", code], env=env, capture_output=True, text=True,
+                       timeout=timeout, cwd=target)
+    assert p.returncode == 0, p.stdout[-2000:] + p.stderr[-3000:]
+    line = [ln for ln in p.stdout.splitlines() if ln.startswith("RESULT")][-1]
+    return json.loads(line[6:])
+
+
+def test_entry_point_resolves_to_installed_backend(installed):
+    code = r"""
+import json
+from importlib.metadata import entry_points
+eps = [e for e in entry_points(group="tike.PtychoBackend") if e.name == "cudafft"]
+assert len(eps) == 1, eps
+cls = eps[0].load()
+import libtike.cufft, libtike.cufft.ptycho as m
+print("RESULT" + json.dumps({"value": eps[0].value, "cls": cls.__name__, "module": cls.__module__,
+                             "file": m.__file__, "is": cls is libtike.cufft.PtychoCuFFT,
+                             "version": libtike.cufft.__version__}))
+"""
+    r = _run_installed(installed, code)
+    assert r["value"] == "libtike.cufft.ptycho:PtychoCuFFT"   # setup.py:27-31 of the reference
+    assert r["cls"] == "PtychoCuFFT" and r["module"] == "libtike.cufft.ptycho" and r["is"]
+    assert os.path.realpath(r["file"]).startswith(os.path.realpath(installed))  # the installed copy
+    assert r["version"].startswith("0.4.0")
+
+
+@pytest.mark.gpu
+def test_entry_point_backend_runs_c1(installed):
+    """C1 (the reference's tests/test_adjoint.py:15-59) through the class the entry point hands out."""
+    code = r"""
+import json
+import numpy as np
+from importlib.metadata import entry_points
+import workloads
+from oracle import numpy_ptycho as O
+cls = [e for e in entry_points(group="tike.PtychoBackend") if e.name == "cudafft"][0].load()
+c = workloads.c1_adjoint(nscan=100)
+psi, scan, prb = c["psi"], c["scan"], c["probe"]
+with cls(nscan=100, probe_shape=128, detector_shape=128, ntheta=1, nz=276, n=600) as slv:
+    t1 = slv.fwd_ptycho_batch(psi, scan, prb[:, 0])
+    t2 = slv.adj_ptycho_batch(t1, scan, prb[:, 0])
+    t3 = slv.adj_ptycho_batch_prb(t1, scan, psi)
+a = np.sum(psi * np.conj(t2)); b = np.sum(t1 * np.conj(t1)); c_ = np.sum(prb[:, 0] * np.conj(t3))
+g0 = O.fwd(psi, scan, prb[:, 0], 128)
+e = float(np.linalg.norm(t1 - g0) / np.linalg.norm(g0))
+print("RESULT" + json.dumps({"a": [a.real, a.imag], "b": [b.real, b.imag], "c": [c_.real, c_.imag], "e": e}))
+"""
+    r = _run_installed(installed, code)
+    a, b, c = (complex(*r[k]) for k in "abc")
+    assert abs(a - b) / abs(a) < 1e-5 and abs(a - c) / abs(a) < 1e-5
+    assert abs(a.real - 60304.69) < 0.5   # the value the reference's test prints
+    assert r["e"] < 1e-5
+
+
+def test_pybind11_module_surface():
+    """Compiled option B: same class surface as the reference's module (no GPU needed to import)."""
+    sys.path.insert(0, ROOT)
+    import __graft_entry__
+    __graft_entry__.build()
+    from libtike.cufft import ptychofft_pb
+    cls = ptychofft_pb.ptychofft
+    for name in ("ptheta", "nz", "n", "nscan", "ndet", "nprb", "fwd", "adj", "free"):
+        assert hasattr(cls, name), name
+    import torch
+    if not torch.cuda.is_available():
+        with pytest.raises(RuntimeError):   # no device: fails loudly, like the ctypes class
+            cls(ptheta=1, nz=276, n=600, nscan=10, detector_shape=128, probe_shape=128)
+
+
+@pytest.mark.gpu
+def test_pybind11_raw_pointer_class_surface():
+    """tests/test_gpu_operators.py::test_raw_pointer_class_surface through the pybind11 module."""
+    import torch
+    import workloads
+    from oracle import numpy_ptycho as O
+    from libtike.cufft import ptychofft_pb
+    from util import rel_l2
+    o = ptychofft_pb.ptychofft(ptheta=1, nz=276, n=600, nscan=10, detector_shape=128, probe_shape=128)
+    assert (o.ptheta, o.nz, o.n, o.nscan, o.ndet, o.nprb) == (1, 276, 600, 10, 128, 128)
+    with pytest.raises(AttributeError):
+        o.ndet = 3
+    c = workloads.c1_adjoint(nscan=10)
+    psi, scan, prb = (torch.from_numpy(np.ascontiguousarray(x)).cuda()
+                      for x in (c["psi"], c["scan"], c["probe"][:, 0]))
+    g = torch.zeros((1, 10, 128, 128), dtype=torch.complex64, device="cuda")
+    f = torch.zeros_like(psi)
+    q = torch.zeros_like(prb)
+    torch.cuda.synchronize()  # the module launches on the legacy default stream, like the reference
+    o.fwd(g.data_ptr(), psi.data_ptr(), scan.data_ptr(), prb.data_ptr())
+    o.adj(f.data_ptr(), g.data_ptr(), scan.data_ptr(), prb.data_ptr(), 0)
+    o.adj(psi.data_ptr(), g.data_ptr(), scan.data_ptr(), q.data_ptr(), 1)
+    torch.cuda.synchronize()
+    g0 = O.fwd(c["psi"], c["scan"], c["probe"][:, 0], 128)
+    assert rel_l2(g.cpu().numpy(), g0) < 1e-5
+    assert rel_l2(f.cpu().numpy(), O.adj(g0, c["scan"], c["probe"][:, 0], 276, 600)) < 1e-5
+    assert rel_l2(q.cpu().numpy(), O.adj_probe(g0, c["scan"], c["psi"], 128)) < 1e-5
+    o.free()
+    o.free()  # idempotent (ptychofft.cu:49-57)
+    with pytest.raises(RuntimeError):
+        o.fwd(g.data_ptr(), psi.data_ptr(), scan.data_ptr(), prb.data_ptr())
+
+
+class _CudaArray(object):
+    """A device array that is NOT a torch tensor: only `__cuda_array_interface__` (v3), the protocol
+    CuPy arrays -- what the reference's callers pass (ptycho.py:80-123) -- expose."""
+
+    def __init__(self, t):
+        self._keep = t
+        typestr = {"torch.complex64": "<c8", "torch.float32": "<f4"}[str(t.dtype)]
+        self.__cuda_array_interface__ = {"shape": tuple(t.shape), "typestr": typestr,
+                                         "data": (t.data_ptr(), False), "version": 3,
+                                         "strides": None, "stream": None}
+
+
+@pytest.mark.gpu
+def test_cuda_array_interface_inputs():
+    import torch
+    import workloads
+    import libtike.cufft as pt
+    from oracle import numpy_ptycho as O
+    from util import rel_l2
+    c = workloads.c1_adjoint(nscan=9)
+    psi, scan, prb = (torch.from_numpy(np.ascontiguousarray(x)).cuda()
+                      for x in (c["psi"], c["scan"], c["probe"][:, 0]))
+    with pt.PtychoCuFFT(9, 128, 128, 1, 276, 600) as slv:
+        g = slv.fwd(_CudaArray(psi), _CudaArray(scan), _CudaArray(prb))
+        f = slv.adj(_CudaArray(g), _CudaArray(scan), _CudaArray(prb))
+        q = slv.adj_probe(_CudaArray(g), _CudaArray(scan), _CudaArray(psi))
+        with pytest.raises(AssertionError):   # dtype asserts of ptycho.py:82-84 still bite
+            slv.fwd(_CudaArray(psi), _CudaArray(scan), _CudaArray(scan))
+    g0 = O.fwd(c["psi"], c["scan"], c["probe"][:, 0], 128)
+    assert rel_l2(g.cpu().numpy(), g0) < 1e-5
+    assert rel_l2(f.cpu().numpy(), O.adj(g0, c["scan"], c["probe"][:, 0], 276, 600)) < 1e-5
+    assert rel_l2(q.cpu().numpy(), O.adj_probe(g0, c["scan"], c["psi"], 128)) < 1e-5
