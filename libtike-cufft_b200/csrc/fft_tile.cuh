@@ -245,6 +245,28 @@ struct Plan<7> {
   static constexpr int XG2 = 0;
 };
 
+// N = 128, geometry of the pipelined kernel (ptycho_pipe.cuh): same stages as Plan<7>, but the exchange
+// tile holds ONE float per element (real and imaginary planes change ownership one after the other),
+// i.e. 32-bit accesses with 32 lanes per wavefront: row pitch 132 = 4 mod 32, skew(x) = (x >> 5) & 3,
+// and stage 0 takes y2 instead of y0 as its fifth lane bit, so that in every stage the five lane bits
+// move the bank index by five distinct powers of two (S0: 1,2,4,8,16; S1: 1,2,4,8,16; S2: 16,1,4,8,2).
+struct WP128_1 {  // stage 0: free bits x[3:0], y[4:0]; lanes x0..x3, y2; then y0, y1, y3, y4
+  static constexpr int bit(int j) {
+    return j < 4 ? j : j == 4 ? (16 + 2) : j == 5 ? (16 + 0) : j == 6 ? (16 + 1) : (16 + (j - 7 + 3));
+  }
+};
+struct Plan7P {
+  static constexpr int L = 7, N = 128, LX = 7, LY = 7, NX = 128, NY = 128, RC = 1, LC = 0;
+  static constexpr int E = 32, NT = NX * NY / E, NSTAGE = 3, WBITS = 9;
+  using S0 = Stage<4, 3, 5, 2, 0, NoBatch, WP128_1>;
+  using S1 = Stage<2, 2, 2, 3, 0, NoBatch, W128_2>;
+  using S2 = Stage<0, 2, 0, 2, 1, B128_3, W128_3>;
+  static constexpr int RS = 132;  // floats; 4 mod 32
+  static PTX_HD constexpr int skew(int x) { return (x >> 5) & 3; }
+  static constexpr int XG2 = 0;
+};
+
+
 // N = 64: 128 threads x 32 elements; x = 3+3 bits, y = 2+2+2 (last stage: radix-4 on y, 8 batches).
 struct W64_1 {  // active x[5:3], y[5:4]; free: x[2:0], y[3:0]; lanes x0,x1,y0,y1,x2
   static constexpr int bit(int j) {

@@ -219,8 +219,11 @@ static int plan_init(ptx_plan* p) {
   CUDA_TRY(cudaMemcpy(p->tw, tw.data(), tw.size() * sizeof(float2), cudaMemcpyHostToDevice));
   // opt in to the large dynamic shared-memory carve-out for every kernel of this size class
   for (int k = 0; k < K_COUNT; ++k) {
+    if (!ops->kernels[k]) continue;
     const bool reg = k == K_REG_OBJ || k == K_REG_FOURIER || k == K_REG_REAL;
-    const size_t bytes = reg && ops->smem_bytes_reg > ops->smem_bytes ? ops->smem_bytes_reg : ops->smem_bytes;
+    const bool pipe = k >= K_PIPE_GAUSS && k <= K_PIPEMC_POIS;
+    const size_t bytes = pipe ? ops->smem_bytes_pipe
+                              : reg && ops->smem_bytes_reg > ops->smem_bytes ? ops->smem_bytes_reg : ops->smem_bytes;
     CUDA_TRY(cudaFuncSetAttribute(ops->kernels[k], cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes));
   }
   // persistent grid: as many CTAs as fit at once
@@ -235,13 +238,16 @@ static int plan_init(ptx_plan* p) {
   CUDA_TRY(cudaMalloc(&p->slots, ops->slots_per_cta * p->grid * sizeof(double)));
   if (ops->frame_per_cta) {
     // N > 128: the per-CTA staging frames (8 N^2 bytes each) are written and read back twice per
-    // pattern.  They are one contiguous array so that a persisting-L2 access-policy window can pin
-    // them next to the streaming measured data (256^2: 148 x 512 KB = 76 MB of the 126 MB L2);
-    // without it ncu showed 4x the algorithmic DRAM traffic (profiles/r01l_bench_grad_c4_ncu.txt).
+    // pattern; one contiguous array.  PTX_L2_PERSIST=1 pins it in a persisting-L2 access-policy window
+    // (experiment, OFF by default).  Measured on B200 (profiles/r02a_l2_window.txt): frame READS already
+    // hit L2 (85 %), every frame WRITE is written back to DRAM with or without the window (the L2
+    // cleans dirty lines eagerly; DRAM is 17 % busy, not the limiter), kernel times move by +-4 % at
+    // 256^2 and get 15-60 % WORSE at 512^2, and the 83 MB set-aside slows every other kernel of the
+    // process that lives on L2 reuse.
     const size_t bytes = ops->frame_per_cta * p->grid * sizeof(float2);
     CUDA_TRY(cudaMalloc(&p->frame, bytes));
     const char* e = getenv("PTX_L2_PERSIST");
-    if (!(e && !strcmp(e, "0"))) {
+    if (e && !strcmp(e, "1")) {
       int max_persist = 0, max_window = 0;
       cudaDeviceGetAttribute(&max_persist, cudaDevAttrMaxPersistingL2CacheSize, p->device);
       cudaDeviceGetAttribute(&max_window, cudaDevAttrMaxAccessPolicyWindowSize, p->device);
@@ -348,8 +354,10 @@ static int launch(ptx_plan* p, int kid, PassArgs& a, cudaStream_t st) {
   cudaLaunchConfig_t cfg;
   memset(&cfg, 0, sizeof(cfg));
   cfg.gridDim = dim3(grid);
-  cfg.blockDim = dim3(ops->NT);
-  cfg.dynamicSmemBytes = reg ? ops->smem_bytes_reg : nodata ? ops->smem_bytes_nodata : ops->smem_bytes;
+  const bool pipe = kid >= K_PIPE_GAUSS && kid <= K_PIPEMC_POIS;
+  cfg.blockDim = dim3(pipe ? ops->NT_pipe : ops->NT);
+  cfg.dynamicSmemBytes = pipe ? ops->smem_bytes_pipe
+                              : reg ? ops->smem_bytes_reg : nodata ? ops->smem_bytes_nodata : ops->smem_bytes;
   cfg.stream = st;
   cudaLaunchAttribute attr[1];
   if (p->l2_window) {  // keep the staging frames in the persisting part of L2; everything else streams
@@ -601,6 +609,16 @@ int ptx_cg_grad(ptx_plan* p, int what, const void* psi, const void* scan, const 
   a.grad_ts = grad_angle_stride ? grad_angle_stride : pp;
   a.far = (float2*)far_out;
   cudaStream_t st = (cudaStream_t)stream;
+  // object gradient of the 128^2 plan: the warp-specialised, pipelined kernel (PTX_PIPE=0: the
+  // single-role kernel, kept for A/B measurements and as the structure of the other plans)
+  static const bool use_pipe = []() {
+    const char* e = getenv("PTX_PIPE");
+    return !(e && !strcmp(e, "0"));
+  }();
+  if (what == 0 && use_pipe && p->ops->NT_pipe && (model == PTX_MODEL_GAUSSIAN || model == PTX_MODEL_POISSON))
+    return launch(p, (model == PTX_MODEL_GAUSSIAN ? (far_out ? K_PIPEC_GAUSS : K_PIPE_GAUSS)
+                                                  : (far_out ? K_PIPEC_POIS : K_PIPE_POIS)) +
+                         (inten_in ? K_PIPEM_GAUSS - K_PIPE_GAUSS : 0), a, st);
   if (model == PTX_MODEL_GAUSSIAN)
     return launch(p, far_out ? (what == 0 ? K_GRADC_GAUSS_OBJ : K_GRADC_GAUSS_PRB)
                              : (what == 0 ? K_GRAD_GAUSS_OBJ : K_GRAD_GAUSS_PRB), a, st);

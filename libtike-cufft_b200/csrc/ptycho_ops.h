@@ -61,6 +61,9 @@ enum KernelId {
   K_REG_OBJ, K_REG_FOURIER, K_REG_REAL,
   K_GRADC_GAUSS_OBJ, K_GRADC_GAUSS_PRB, K_GRADC_POIS_OBJ, K_GRADC_POIS_PRB,  // + far-field cache output
   K_LSAB_GAUSS, K_LSAB_POIS,  // + the next iteration's a, b sums of every candidate
+  // warp-specialised, pipelined object-gradient kernels (ptycho_pipe.cuh; 128^2 plan only, else null)
+  K_PIPE_GAUSS, K_PIPEC_GAUSS, K_PIPE_POIS, K_PIPEC_POIS,      // I = |F|^2 (one mode)
+  K_PIPEM_GAUSS, K_PIPEMC_GAUSS, K_PIPEM_POIS, K_PIPEMC_POIS,  // I = the summed intensity map (several modes)
   K_COUNT
 };
 
@@ -69,6 +72,8 @@ struct PlanOps {
   size_t smem_bytes;       // dynamic shared memory of the kernels that read measured data
   size_t smem_bytes_nodata;  // ... of the others (no data tile: more of the SM's SRAM stays L1)
   size_t smem_bytes_reg;     // ... of the position-correction kernels
+  int NT_pipe;               // threads per CTA of the pipelined kernels (0: none for this plan)
+  size_t smem_bytes_pipe;    // ... and their dynamic shared memory
   size_t frame_per_cta, stash_per_cta;  // float2 (frame: 0 for single-tile plans)
   size_t accp_per_cta;     // floats
   size_t slots_per_cta;    // doubles

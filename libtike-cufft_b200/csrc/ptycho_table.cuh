@@ -31,6 +31,12 @@ void fill_ops_base(PlanOps& ops) {
   ops.slots_per_cta = Scratch<P>::SLOTS;
   ops.tw_total = TwLayout<P>::TOTAL;
   ops.fill_tw = fill_tw_host<P>;
+  ops.NT_pipe = 0;
+  ops.smem_bytes_pipe = 0;
+  for (int k = K_PIPE_GAUSS; k <= K_PIPEMC_POIS; ++k) {
+    ops.kernels[k] = nullptr;
+    ops.names[k] = "(none)";
+  }
   ops.patch_w = Patch<P>::TMA ? Patch<P>::W : 0;
   ops.patch_h = Patch<P>::TMA ? Patch<P>::H : 0;
   PTX_SET(K_FWD, k_fwd<P>)

@@ -198,11 +198,20 @@ class RefCGPtychoSolver(RefPtychoFFT):
     """torch restatement of CGPtychoSolver (ptycho.py:250-488)."""
 
     position_correction = False
+    cdtype = torch.complex64
+    rdtype = torch.float32
+    #: optional list of raw line-search results, consumed in call order, that REPLACE the decisions
+    #: (used to run a second arithmetic -- e.g. the float64 referee -- along the same trajectory)
+    forced_steps = None
 
     @staticmethod
-    def line_search_sqr(f, p1, p2, p3, step_length=1, step_shrink=0.5, trials=None):
+    def line_search_sqr(f, p1, p2, p3, step_length=1, step_shrink=0.5, trials=None, forced=None):
         """ptycho.py:253-281; `trials` (diagnostics) collects (f(p1), [(step, f(step)), ...], result)."""
         assert step_shrink > 0 and step_shrink < 1
+        if forced is not None:
+            if trials is not None:
+                trials.append((float("nan"), [], forced))
+            return forced
         m = 0
         fp1 = f(p1)
         seen = []
@@ -240,6 +249,10 @@ class RefCGPtychoSolver(RefPtychoFFT):
                   "iteration, step size object, step size probe, function min")
         gammaprb = 0
         trials = []
+        forced = list(self.forced_steps) if self.forced_steps else None
+
+        def next_forced():
+            return forced.pop(0) if forced else None
         for i in range(piter):
             absfpsi = data * 0
             for k in range(probe.shape[1]):
@@ -249,7 +262,7 @@ class RefCGPtychoSolver(RefPtychoFFT):
             b = torch.sum(absfpsi)
             probe *= (a / b)
             absfpsi *= (a / b) ** 2
-            gradpsi = torch.zeros([self.ptheta, self.nz, self.n], dtype=torch.complex64,
+            gradpsi = torch.zeros([self.ptheta, self.nz, self.n], dtype=self.cdtype,
                                   device="cuda")
             if model == "gaussian":
                 for k in range(probe.shape[1]):
@@ -279,7 +292,7 @@ class RefCGPtychoSolver(RefPtychoFFT):
                 p1 += torch.abs(tmp1) ** 2
                 p2 += torch.abs(tmp2) ** 2
                 p3 += 2 * (tmp1.real * tmp2.real + tmp1.imag * tmp2.imag)
-            gammapsi = 0.5 * self.line_search_sqr(minf, p1, p2, p3, trials=trials)
+            gammapsi = 0.5 * self.line_search_sqr(minf, p1, p2, p3, trials=trials, forced=next_forced())
             if self.position_correction and i > 0:  # ptycho.py:398-403
                 tmp1 = self.fwd(psi, scan, probe[:, 0] * 0 + 1)[0]
                 tmp2 = self.fwd(psi + gammapsi * dpsi, scan, probe[:, 0] * 0 + 1)[0]
@@ -327,7 +340,7 @@ class RefCGPtychoSolver(RefPtychoFFT):
                     p2 = torch.abs(tmp2) ** 2
                     p3 = 2 * (tmp1.real * tmp2.real + tmp1.imag * tmp2.imag)
                     gammaprb = 0.5 * self.line_search_sqr(minf, p1, p2, p3, step_length=1,
-                                                          trials=trials)
+                                                          trials=trials, forced=next_forced())
                     probe[:, m] = probe[:, m] + gammaprb * dprb[:, m]
             if history is not None:
                 history.append((i, float(gammapsi), float(gammaprb), float(minf(absfpsi))))
@@ -343,10 +356,111 @@ class RefCGPtychoSolver(RefPtychoFFT):
         probe = probe.copy()
         for k in range(0, scan.shape[0] // self.ptheta):
             ids = np.arange(k * self.ptheta, (k + 1) * self.ptheta)
-            psi_gpu = torch.from_numpy(psi[ids]).cuda()
-            scan_gpu = torch.from_numpy(scan[ids]).cuda()
-            prb_gpu = torch.from_numpy(probe[ids]).cuda()
-            data_gpu = torch.from_numpy(data[ids]).cuda()
+            psi_gpu = torch.from_numpy(psi[ids]).cuda().to(self.cdtype)
+            scan_gpu = torch.from_numpy(scan[ids]).cuda()  # positions stay float32 data in every arithmetic
+            prb_gpu = torch.from_numpy(probe[ids]).cuda().to(self.cdtype)
+            data_gpu = torch.from_numpy(data[ids]).cuda().to(self.rdtype)
             result = self.run(data_gpu, psi_gpu, scan_gpu, prb_gpu, **kwargs)
             psi[ids], probe[ids] = result["psi"].cpu().numpy(), result["probe"].cpu().numpy()
         return {"psi": psi, "probe": probe}
+
+
+class F64PtychoOps(object):
+    """The operators of kernels.cu:19-107 + ptychofft.cu:60-88 restated in torch with float64 /
+    complex128 arithmetic on the GPU (cuFFT in double precision): the EXACT answer, to ~1e-15, that
+    both fp32 implementations -- the reference's cuFFT path and the sm_100a kernels -- are measured
+    against where the reference's formulas amplify rounding (tests/, tests/tools/).  Same statements
+    as oracle/numpy_ptycho.py under `float64_arithmetic()`, which pins it (tests/test_gpu_f64_oracle.py);
+    positions must lie in the reference's valid domain (no zero extension here)."""
+
+    def __init__(self, nscan, probe_shape, detector_shape, ntheta, nz, n):
+        self.ptheta, self.nz, self.n = ntheta, nz, n
+        self.nscan, self.ndet, self.nprb = nscan, detector_shape, probe_shape
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *exc):
+        pass
+
+    def free(self):
+        pass
+
+    @staticmethod
+    def _split(scan_t):
+        r, c = scan_t[:, 0].double(), scan_t[:, 1].double()
+        R, C = torch.trunc(r), torch.trunc(c)
+        keep = ~((R < 0) | (C < 0))
+        return (torch.where(keep, R, 0 * R).long(), torch.where(keep, C, 0 * C).long(), r - R, c - C, keep)
+
+    def _patches(self, psi_t, scan_t):
+        P = self.nprb
+        R, C, rho, gam, keep = self._split(scan_t)
+        ar = torch.arange(P + 1, device=psi_t.device)
+        a = psi_t[(R[:, None] + ar)[:, :, None], (C[:, None] + ar)[:, None, :]]
+        w = lambda x: x[:, None, None]  # noqa: E731
+        out = (a[:, :-1, :-1] * w((1 - gam) * (1 - rho)) + a[:, :-1, 1:] * w(gam * (1 - rho))
+               + a[:, 1:, :-1] * w((1 - gam) * rho) + a[:, 1:, 1:] * w(gam * rho))
+        out[~keep] = 0
+        return out, keep
+
+    def fwd(self, psi, scan, probe):
+        psi, probe = psi.to(torch.complex128), probe.to(torch.complex128)
+        N, P = self.ndet, self.nprb
+        o = (N - P) // 2
+        g = torch.zeros((self.ptheta, self.nscan, N, N), dtype=torch.complex128, device=psi.device)
+        for t in range(self.ptheta):
+            patches, _ = self._patches(psi[t], scan[t])
+            near = torch.zeros((self.nscan, N, N), dtype=torch.complex128, device=psi.device)
+            near[:, o:o + P, o:o + P] = patches * probe[t][None] / N
+            g[t] = torch.fft.fft2(near)
+        return g
+
+    def _near(self, g_t):
+        N, P = self.ndet, self.nprb
+        o = (N - P) // 2
+        return torch.fft.ifft2(g_t.to(torch.complex128), norm="forward")[:, o:o + P, o:o + P]
+
+    def adj(self, farplane, scan, probe):
+        probe = probe.to(torch.complex128)
+        P = self.nprb
+        out = torch.zeros((self.ptheta, self.nz, self.n), dtype=torch.complex128, device=farplane.device)
+        ar = torch.arange(P, device=farplane.device)
+        for t in range(self.ptheta):
+            R, C, rho, gam, keep = self._split(scan[t])
+            tmp = self._near(farplane[t]) * torch.conj(probe[t])[None] / self.ndet
+            tmp[~keep] = 0
+            rows, cols = (R[:, None] + ar)[:, :, None], (C[:, None] + ar)[:, None, :]
+            re, im = torch.zeros_like(out[t].real), torch.zeros_like(out[t].real)
+            w = lambda x: x[:, None, None]  # noqa: E731
+            for dy, dx, wt in ((0, 0, (1 - gam) * (1 - rho)), (0, 1, gam * (1 - rho)),
+                               (1, 0, (1 - gam) * rho), (1, 1, gam * rho)):
+                v = tmp * w(wt)
+                idx = ((rows + dy).expand(-1, P, P), (cols + dx).expand(-1, P, P))
+                re.index_put_(idx, v.real, accumulate=True)
+                im.index_put_(idx, v.imag, accumulate=True)
+            out[t] = torch.complex(re, im)
+        return out
+
+    def adj_probe(self, farplane, scan, psi):
+        psi = psi.to(torch.complex128)
+        out = torch.zeros((self.ptheta, self.nprb, self.nprb), dtype=torch.complex128, device=psi.device)
+        for t in range(self.ptheta):
+            patches, keep = self._patches(psi[t], scan[t])
+            near = self._near(farplane[t])
+            near[~keep] = 0
+            out[t] = (near * torch.conj(patches)).sum(0) / self.ndet
+        return out
+
+
+class F64CGPtychoSolver(F64PtychoOps, RefCGPtychoSolver):
+    """The restated solver (ptycho.py:250-488) over the float64 operators: the referee trajectory."""
+    cdtype = torch.complex128
+    rdtype = torch.float64
+
+    def __init__(self, *args):
+        F64PtychoOps.__init__(self, *args)
+
+    def run_batch(self, data, psi, scan, probe, **kwargs):
+        return RefCGPtychoSolver.run_batch(self, data.astype(np.float64), psi.astype(np.complex128),
+                                           scan, probe.astype(np.complex128), **kwargs)

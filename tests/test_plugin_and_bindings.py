@@ -84,7 +84,8 @@ with cls(nscan=100, probe_shape=128, detector_shape=128, ntheta=1, nz=276, n=600
 a = np.sum(psi * np.conj(t2)); b = np.sum(t1 * np.conj(t1)); c_ = np.sum(prb[:, 0] * np.conj(t3))
 g0 = O.fwd(psi, scan, prb[:, 0], 128)
 e = float(np.linalg.norm(t1 - g0) / np.linalg.norm(g0))
-print("RESULT" + json.dumps({"a": [a.real, a.imag], "b": [b.real, b.imag], "c": [c_.real, c_.imag], "e": e}))
+print("RESULT" + json.dumps({"a": [float(a.real), float(a.imag)], "b": [float(b.real), float(b.imag)],
+                             "c": [float(c_.real), float(c_.imag)], "e": e}))
 """
     r = _run_installed(installed, code)
     a, b, c = (complex(*r[k]) for k in "abc")
