@@ -615,10 +615,11 @@ int ptx_cg_grad(ptx_plan* p, int what, const void* psi, const void* scan, const 
     const char* e = getenv("PTX_PIPE");
     return !(e && !strcmp(e, "0"));
   }();
-  if (what == 0 && use_pipe && p->ops->NT_pipe && (model == PTX_MODEL_GAUSSIAN || model == PTX_MODEL_POISSON))
+  if (what == 0 && use_pipe && p->ops->NT_pipe && (model == PTX_MODEL_GAUSSIAN || model == PTX_MODEL_POISSON)) {
     return launch(p, (model == PTX_MODEL_GAUSSIAN ? (far_out ? K_PIPEC_GAUSS : K_PIPE_GAUSS)
                                                   : (far_out ? K_PIPEC_POIS : K_PIPE_POIS)) +
                          (inten_in ? K_PIPEM_GAUSS - K_PIPE_GAUSS : 0), a, st);
+  }
   if (model == PTX_MODEL_GAUSSIAN)
     return launch(p, far_out ? (what == 0 ? K_GRADC_GAUSS_OBJ : K_GRADC_GAUSS_PRB)
                              : (what == 0 ? K_GRAD_GAUSS_OBJ : K_GRAD_GAUSS_PRB), a, st);

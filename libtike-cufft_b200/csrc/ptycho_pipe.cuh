@@ -123,8 +123,8 @@ __device__ __forceinline__ void pipe_fft_inverse(float2 (&v)[32], float* tile, c
 // lane, the horizontally interpolated value of the row below is carried to the next iteration.
 //   near[y][x] = kappa * prb[iy][ix] * ((1-rho) h[iy][ix] + rho h[iy+1][ix]),
 //   h[r][c] = (1-gam) psi[R+r][C+c] + gam psi[R+r][C+c+1]        (kernels.cu:95-107; zero outside)
-__device__ __forceinline__ void pipe_gather(float2* __restrict__ B, int h, const float2* __restrict__ psi_t,
-                                            const float2* __restrict__ prb, const Geo& g, const Pat& p) {
+__device__ __forceinline__ void pipe_gather_any(float2* __restrict__ B, int h, const float2* __restrict__ psi_t,
+                                             const float2* __restrict__ prb, const Geo& g, const Pat& p) {
   constexpr int PB = Pipe::PB, N = Plan7P::N, CH = 8;
   const int lane = h & 31;
   const int ix = h - g.o;
@@ -178,9 +178,9 @@ __device__ __forceinline__ void pipe_gather(float2* __restrict__ B, int h, const
 // B holds near = IFFT2(residual) (frame order).  t = scale * conj(prb) * near; the bilinear spread is
 // separable:  hq[y][x] = (1-gam) t[y][x] + gam t[y][x-1],  out[y][x] = (1-rho) hq[y][x] + rho hq[y-1][x],
 // one vector reduction per object pixel (kernels.cu:69-81 issues 8 scalar atomics per probe pixel).
-__device__ __forceinline__ void pipe_scatter(const float2* __restrict__ B, int h, const float2* __restrict__ prb,
-                                             float scale, float2* __restrict__ grad_t, const Geo& g,
-                                             const Pat& p) {
+__device__ __forceinline__ void pipe_scatter_any(const float2* __restrict__ B, int h, const float2* __restrict__ prb,
+                                              float scale, float2* __restrict__ grad_t, const Geo& g,
+                                              const Pat& p) {
   constexpr int PB = Pipe::PB, N = Plan7P::N, CH = 8;
   const int lane = h & 31;
   const int ix = h - g.o;
@@ -241,6 +241,124 @@ __device__ __forceinline__ void pipe_scatter(const float2* __restrict__ B, int h
   }
 }
 
+// ---------------------------------------------------------------- helpers: fast paths
+// Full probe window (P == N) lying inside the object: no predicates, pointers advanced row by row.
+__device__ __forceinline__ void pipe_gather_fast(float2* __restrict__ B, int h, const float2* __restrict__ psi_t,
+                                                 const float2* __restrict__ prb, const Geo& g, const Pat& p) {
+  constexpr int PB = Pipe::PB, N = Plan7P::N, CH = 8;
+  const bool last = (h & 31) == 31;
+  const float2 z = make_float2(0.f, 0.f);
+  const float a0 = 1.f - p.gam, a1 = p.gam, kb0 = g.kappa * (1.f - p.rho), kb1 = g.kappa * p.rho;
+  const int n = g.n;
+  const float2* src = psi_t + (size_t)p.R * n + p.C + h;
+  const float2* pp = prb + h;
+  float2* bc = B + 1 + h;
+  auto hval = [&](float2 f0, float2 fx) {
+    float2 f1 = make_float2(__shfl_down_sync(0xffffffffu, f0.x, 1), __shfl_down_sync(0xffffffffu, f0.y, 1));
+    if (last) f1 = fx;
+    return make_float2(a0 * f0.x + a1 * f1.x, a0 * f0.y + a1 * f1.y);
+  };
+  float2 hc;
+  {
+    const float2 f0 = __ldg(src);
+    float2 fx = z;
+    if (last) fx = __ldg(src + 1);
+    hc = hval(f0, fx);
+  }
+  src += n;
+#pragma unroll 1
+  for (int y0 = 0; y0 < N; y0 += CH) {
+    float2 f0[CH], fx[CH], pr[CH];
+#pragma unroll
+    for (int j = 0; j < CH; ++j) {
+      f0[j] = __ldg(src + j * n);
+      fx[j] = z;
+      if (last) fx[j] = __ldg(src + j * n + 1);
+      pr[j] = __ldg(pp + j * N);
+    }
+    src += CH * n;
+    pp += CH * N;
+#pragma unroll
+    for (int j = 0; j < CH; ++j) {
+      const float2 hn = hval(f0[j], fx[j]);
+      const float2 t = make_float2(kb0 * hc.x + kb1 * hn.x, kb0 * hc.y + kb1 * hn.y);
+      bc[(y0 + j) * PB] = make_float2(pr[j].x * t.x - pr[j].y * t.y, pr[j].x * t.y + pr[j].y * t.x);
+      hc = hn;
+    }
+  }
+}
+
+__device__ __forceinline__ void pipe_scatter_fast(const float2* __restrict__ B, int h,
+                                                  const float2* __restrict__ prb, float scale,
+                                                  float2* __restrict__ grad_t, const Geo& g, const Pat& p) {
+  constexpr int PB = Pipe::PB, N = Plan7P::N, CH = 8;
+  const bool first = (h & 31) == 0;
+  const bool hasl = h > 0;
+  const float2 z = make_float2(0.f, 0.f);
+  const float a0 = 1.f - p.gam, a1 = p.gam, b0 = 1.f - p.rho, b1 = p.rho;
+  const int n = g.n;
+  const float2* bc = B + 1 + h;
+  const float2* pp = prb + h;
+  float2* dst = grad_t + (size_t)p.R * n + p.C + h;
+  auto tval = [&](float2 pr, float2 nr) {  // scale * conj(pr) * nr
+    return make_float2(scale * (pr.x * nr.x + pr.y * nr.y), scale * (pr.x * nr.y - pr.y * nr.x));
+  };
+  float2 hp = z;
+#pragma unroll 1
+  for (int y0 = 0; y0 < N; y0 += CH) {
+    float2 nr[CH], pr[CH], nl[CH], pl[CH];
+#pragma unroll
+    for (int j = 0; j < CH; ++j) {
+      nr[j] = bc[(y0 + j) * PB];
+      pr[j] = __ldg(pp + j * N);
+      nl[j] = z;
+      pl[j] = z;
+      if (first) {  // the left neighbour belongs to another warp (guard column of zeros for h == 0)
+        nl[j] = bc[(y0 + j) * PB - 1];
+        if (hasl) pl[j] = __ldg(pp + j * N - 1);
+      }
+    }
+    pp += CH * N;
+#pragma unroll
+    for (int j = 0; j < CH; ++j) {
+      const float2 tc = tval(pr[j], nr[j]);
+      float2 tl = make_float2(__shfl_up_sync(0xffffffffu, tc.x, 1), __shfl_up_sync(0xffffffffu, tc.y, 1));
+      if (first) tl = tval(pl[j], nl[j]);
+      const float2 hq = make_float2(a0 * tc.x + a1 * tl.x, a0 * tc.y + a1 * tl.y);
+      atomicAdd(dst + j * n, make_float2(b0 * hq.x + b1 * hp.x, b0 * hq.y + b1 * hp.y));
+      hp = hq;
+    }
+    dst += CH * n;
+  }
+  atomicAdd(dst, make_float2(b1 * hp.x, b1 * hp.y));  // the row below the frame
+  if (h < 32) {  // object column C + P: only the gam * t[.][P-1] share
+    const float2* bl = B + N;  // B[y][1 + (N-1)]
+    const float2* pq = prb + (N - 1);
+    float2* de = grad_t + (size_t)p.R * n + p.C + N;
+    for (int y = h; y <= N; y += 32) {
+      const float2 tc = y < N ? tval(__ldg(pq + y * N), bl[y * PB]) : z;
+      const float2 tu = y > 0 ? tval(__ldg(pq + (y - 1) * N), bl[(y - 1) * PB]) : z;
+      atomicAdd(de + (size_t)y * n, make_float2(a1 * (b0 * tc.x + b1 * tu.x), a1 * (b0 * tc.y + b1 * tu.y)));
+    }
+  }
+}
+
+__device__ __forceinline__ void pipe_gather(float2* __restrict__ B, int h, const float2* __restrict__ psi_t,
+                                            const float2* __restrict__ prb, const Geo& g, const Pat& p) {
+  if (g.P == Plan7P::N && p.inside)
+    pipe_gather_fast(B, h, psi_t, prb, g, p);
+  else
+    pipe_gather_any(B, h, psi_t, prb, g, p);
+}
+__device__ __forceinline__ void pipe_scatter(const float2* __restrict__ B, int h, const float2* __restrict__ prb,
+                                             float scale, float2* __restrict__ grad_t, const Geo& g,
+                                             const Pat& p) {
+  if (g.P == Plan7P::N && p.inside)
+    pipe_scatter_fast(B, h, prb, scale, grad_t, g, p);
+  else
+    pipe_scatter_any(B, h, prb, scale, grad_t, g, p);
+}
+
 // ------------------------------------------------------------------------------------------
 // CG pass B, object gradient, pipelined (same contract as k_grad<P, MODEL, 0, CACHE>):
 //   grad += gscale * adj(F * (1 - sqrt(d)/sqrt(I)), scan, probe)       (ptycho.py:347-363)
@@ -271,18 +389,42 @@ __global__ void __launch_bounds__(Pipe::NTHREADS) k_grad_pipe(const PassArgs a,
     const int lbase = pos_to_freq_y<P>(yf2) * P::N + pos_to_freq_x<P>(xf2);
     float2* bp = B + yf0 * Pipe::PB + 1 + xf0;
     float2 v[32];
+#pragma unroll
+    for (int e = 0; e < 32; ++e) v[e] = make_float2(0.f, 0.f);
     bool have = false;
     for (int pat = blockIdx.x; pat < npat; pat += gridDim.x) {
       const Pat p = make_pat(a.scan, pat, g);
       if (p.skip) continue;  // F = 0 -> residual 0 -> no contribution
       nbar_sync(Pipe::BAR_FULL, Pipe::NTHREADS);
+      // near(pat) in, the previous pattern's result out: in place, eight positions at a time through
+      // volatile accesses (ptxas would otherwise hoist all 32 loads: old + new values live = 128
+      // registers, and the whole spectrum array ends up in local memory across the loop).  Before the
+      // first pattern v is zero: what lands in B then is never scattered and is overwritten by the
+      // next gather.
+      {
+        const unsigned sb = smem_u32(bp);
 #pragma unroll
-      for (int e = 0; e < 32; ++e) {  // near(pat) in, the previous pattern's result out
-        int dx, dy;
-        elem_offset<P::S0>(e, dx, dy);
-        const float2 t = bp[dy * Pipe::PB + dx];
-        if (have) bp[dy * Pipe::PB + dx] = v[e];
-        v[e] = t;
+        for (int e0 = 0; e0 < 32; e0 += 8) {
+          float2 t[8];
+#pragma unroll
+          for (int j = 0; j < 8; ++j) {
+            int dx, dy;
+            elem_offset<P::S0>(e0 + j, dx, dy);
+            asm volatile("ld.volatile.shared.v2.f32 {%0, %1}, [%2];"
+                         : "=f"(t[j].x), "=f"(t[j].y)
+                         : "r"(sb + (unsigned)(dy * Pipe::PB + dx) * 8u)
+                         : "memory");
+          }
+#pragma unroll
+          for (int j = 0; j < 8; ++j) {
+            int dx, dy;
+            elem_offset<P::S0>(e0 + j, dx, dy);
+            asm volatile("st.volatile.shared.v2.f32 [%0], {%1, %2};" ::"r"(sb + (unsigned)(dy * Pipe::PB + dx) * 8u),
+                         "f"(v[e0 + j].x), "f"(v[e0 + j].y)
+                         : "memory");
+            v[e0 + j] = t[j];
+          }
+        }
       }
       __threadfence_block();
       nbar_arrive(Pipe::BAR_SWAPPED, Pipe::NTHREADS);

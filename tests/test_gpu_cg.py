@@ -63,7 +63,17 @@ def _assert_parity(got, want, exact_fn, label=""):
     Poisson gradient divides by the far field), so on long or ill-conditioned runs two correct fp32
     implementations drift apart by more than 1e-4.  When the direct comparison exceeds the bar the
     float64 restatement of the same statements (same replayed step decisions) is the referee: the
-    fused solver must be as close to that exact trajectory as the reference's own fp32 run is."""
+    fused solver must be as close to that exact trajectory as the reference's own fp32 run is.
+
+    How close is "as close"?  Measured on B200 (profiles/r02a_cg_parity_probe.txt,
+    profiles/r02c_c5_poisson_seeds.txt): (1) operator by operator the sm_100a kernels are MORE accurate
+    against float64 than the cuFFT path (tests/test_gpu_f64_oracle.py); (2) the per-pixel math is not
+    the cause (IEEE sqrt / division / log build: same distances); (3) the reference does not reproduce
+    ITSELF on these problems -- two runs of its own cuFFT path on the same inputs differ by 6e-4 ... 1e-2
+    (atomic accumulation order; on the long Gaussian runs even its line-search decisions change), and its
+    distance to float64 moves by 1.5x between two runs; (4) over noise realisations the ratio
+    fused-vs-f64 / reference-vs-f64 scatters symmetrically between 0.4 and 1.9.  Hence a factor 3 on one
+    draw; the 1e-4 bar itself applies wherever the reference can meet it against itself."""
     e = {k: rel_l2(got[k], want[k]) for k in ("psi", "probe")}
     print("cg parity", label, "fused vs reference: psi %.2e probe %.2e" % (e["psi"], e["probe"]))
     if max(e.values()) < TOL:
@@ -113,20 +123,21 @@ def _audit_decisions(slv, ref_steps, tie=2e-2, strict=True):
 
 
 @pytest.mark.skipif(not ref_gpu.available(), reason="oracle/_ref not built")
-@pytest.mark.parametrize("nmodes,nscan,model,piter,ndet,noisy", [
-    (1, 100, "gaussian", 8, 128, False),
-    (1, 36, "gaussian", 24, 128, False),
-    (3, 60, "gaussian", 8, 128, False),
-    (1, 49, "poisson", 6, 128, False),
-    (2, 49, "poisson", 6, 64, False),
-    (1, 64, "gaussian", 16, 64, False),
-    (1, 36, "poisson", 4, 64, True),
-    (2, 25, "poisson", 3, 64, True),
-    (1, 16, "gaussian", 4, 256, False),
-    (2, 9, "poisson", 3, 256, True),
-    (1, 9, "gaussian", 3, 512, False),
+@pytest.mark.parametrize("nmodes,nscan,model,piter,ndet,noisy,well", [
+    (1, 100, "gaussian", 8, 128, False, True),
+    (1, 36, "gaussian", 24, 128, False, False),
+    (1, 36, "gaussian", 32, 128, False, False),
+    (3, 60, "gaussian", 8, 128, False, True),
+    (1, 49, "poisson", 6, 128, False, False),
+    (2, 49, "poisson", 6, 64, False, True),
+    (1, 64, "gaussian", 16, 64, False, True),
+    (1, 36, "poisson", 4, 64, True, True),
+    (2, 25, "poisson", 3, 64, True, True),
+    (1, 16, "gaussian", 4, 256, False, True),
+    (2, 9, "poisson", 3, 256, True, True),
+    (1, 9, "gaussian", 3, 512, False, True),
 ])
-def test_cg_vs_reference_gpu(nmodes, nscan, model, piter, ndet, noisy):
+def test_cg_vs_reference_gpu(nmodes, nscan, model, piter, ndet, noisy, well):
     """Reference operators (compiled, cuFFT) + solver restatement vs the fused solver, same GPU.
 
     The line search compares cost sums whose differences can be far below the fp32 resolution of
@@ -146,10 +157,11 @@ def test_cg_vs_reference_gpu(nmodes, nscan, model, piter, ndet, noisy):
                              verbose=False)
         steps = [t[2] for t in ref.last_trials]
 
-    def exact():
-        with O.float64_arithmetic():
-            return O.cg_run(data, psi0, scan, prb0.copy(), piter, model, True,
-                            forced_steps=list(steps))
+    def exact():  # the float64 GPU referee (pinned to the NumPy float64 restatement, test_gpu_f64_oracle.py)
+        with ref_gpu.F64CGPtychoSolver(nscan, ndet, ndet, 1, nz, n) as ex:
+            ex.forced_steps = list(steps)
+            return ex.run_batch(data, psi0, scan, prb0, piter=piter, model=model, recover_prb=True,
+                                verbose=False)
 
     with ReplaySolver(nscan, ndet, ndet, 1, nz, n) as slv:
         slv.forced_steps = list(steps)
@@ -160,9 +172,10 @@ def test_cg_vs_reference_gpu(nmodes, nscan, model, piter, ndet, noisy):
         print("   near ties decided differently:", mism, "of", len(steps))
         slv.forced_steps = None
         free = slv.run_batch(data, psi0, scan, prb0, piter=piter, model=model, recover_prb=True)
-        f_psi, f_prb = rel_l2(free["psi"], got["psi"]), rel_l2(free["probe"], got["probe"])
-        print("   free running vs replayed: psi %.2e probe %.2e" % (f_psi, f_prb))
-        if mism == 0 and same:
+        f_psi, f_prb = rel_l2(free["psi"], want["psi"]), rel_l2(free["probe"], want["probe"])
+        print("   FREE RUNNING vs reference: psi %.2e probe %.2e" % (f_psi, f_prb))
+        if well:  # well-conditioned: the product solver, deciding for itself, meets the bar outright
+            assert same and mism == 0
             assert f_psi < TOL and f_prb < TOL
 
 
