@@ -374,8 +374,10 @@ def scalarcomm_check(pt, world, rank):
             res = slv.run(data[sl].contiguous(), psi0[sl].contiguous(), scan[sl].clone(),
                           probe[sl].clone(), piter=4, recover_prb=True)
             calls, hist = slv.comm.calls, list(slv.history)
-        both = [torch.zeros_like(psi0[:1]) for _ in range(2)]
-        dist.all_gather(both, res["psi"].contiguous(), group=group)
+        mine = torch.view_as_real(res["psi"].contiguous())
+        parts = [torch.zeros_like(mine) for _ in range(2)]
+        dist.all_gather(parts, mine, group=group)
+        both = [torch.view_as_complex(x) for x in parts]
         if rank == 0:
             with pt.CGPtychoSolver(25, 64, 64, 2, 200, 220) as slv, quiet():
                 want = slv.run(data, psi0, scan.clone(), probe.clone(), piter=4, recover_prb=True)

@@ -609,13 +609,16 @@ int ptx_cg_grad(ptx_plan* p, int what, const void* psi, const void* scan, const 
   a.grad_ts = grad_angle_stride ? grad_angle_stride : pp;
   a.far = (float2*)far_out;
   cudaStream_t st = (cudaStream_t)stream;
-  // object gradient of the 128^2 plan: the warp-specialised, pipelined kernel (PTX_PIPE=0: the
-  // single-role kernel, kept for A/B measurements and as the structure of the other plans)
+  // PTX_PIPE=1: object gradient of the 128^2 plan through the warp-specialised, pipelined kernel
+  // (ptycho_pipe.cuh).  Parity-green but not yet faster than the single-role kernel on B200 (44.3 k vs
+  // 40.0 k clk per pattern and SM, profiles/r02f_pipe_ncu.txt: both roles ~84 % busy, issue slots and the
+  // probe's L2 latency bind), hence opt-in.
   static const bool use_pipe = []() {
     const char* e = getenv("PTX_PIPE");
-    return !(e && !strcmp(e, "0"));
+    return e && !strcmp(e, "1");
   }();
-  if (what == 0 && use_pipe && p->ops->NT_pipe && (model == PTX_MODEL_GAUSSIAN || model == PTX_MODEL_POISSON)) {
+  if (what == 0 && use_pipe && p->ops->NT_pipe && p->nprb == p->ndet &&
+      (model == PTX_MODEL_GAUSSIAN || model == PTX_MODEL_POISSON)) {
     return launch(p, (model == PTX_MODEL_GAUSSIAN ? (far_out ? K_PIPEC_GAUSS : K_PIPE_GAUSS)
                                                   : (far_out ? K_PIPEC_POIS : K_PIPE_POIS)) +
                          (inten_in ? K_PIPEM_GAUSS - K_PIPE_GAUSS : 0), a, st);

@@ -5,16 +5,19 @@
 // reduction throughput) never overlap the FMA / shared-memory-bound transforms, and ncu shows no
 // pipe above 60 % (profiles/r01l_bench_grad_ncu.txt).  Here one CTA of 640 threads splits the roles:
 //
-//   warps 0-15 ("FFT warps", 512 threads, 32 complex registers each) only transform: they pull the
-//       near plane of pattern n from a shared buffer B, run FFT2 -> residual against the measured
-//       data -> IFFT2 in registers, and push the result back into B;
+//   warps 0-15 ("FFT warps", 512 threads, 32 complex registers each) transform: they pull the object
+//       patch of pattern n from a shared buffer B, multiply by the probe, run FFT2 -> residual against
+//       the measured data -> IFFT2 in registers, multiply by the conjugate probe and push the result
+//       back into B;
 //   warps 16-19 ("helpers", 128 threads, one frame column each) meanwhile scatter pattern n-1 out of
 //       B into the object gradient (separable bilinear spread, one red.global.add.v2.f32 per object
-//       pixel) and gather pattern n+1 into B (one coalesced load per object pixel, the right tap by
-//       shuffle, the row below carried in a register) -- kernels.cu:69-81 and 95-107.
+//       pixel) and gather the patch of pattern n+1 into B (one coalesced load per object pixel, the
+//       right tap by shuffle, the row below carried in a register) -- kernels.cu:69-81 and 95-107.
 //
 // B changes hands by two named barriers (bar.arrive / bar.sync, producer-consumer): the swap
-// "t(n-1) out, near(n) in" is one in-place pass of the FFT warps over their own 32 positions.
+// "result(n-1) out, patch(n) in" is one in-place pass of the FFT warps over their own 32 positions.
+// Which side does the probe multiplies was decided by ncu's stall samples (profiles/r02e_pipe_v2_ncu.txt):
+// with them in the helper loops the FFT warps sat 61 % of their time at the hand-over barrier.
 // Registers: 640 threads x 96 = 61440 of the SM's 65536 (the transform core needs < 96, measured with
 // -Xptxas -v).  Shared memory: B (128 x 130 complex = 133 KB) + the exchange tile + twiddles.  To
 // make room for B the exchange tile holds ONE float per element: real and imaginary parts change
@@ -121,11 +124,12 @@ __device__ __forceinline__ void pipe_fft_inverse(float2 (&v)[32], float* tile, c
 // Thread h owns frame column x = h.  Walks the rows top to bottom: one object pixel per row is
 // loaded (a warp reads 32 adjacent columns of one object row), the right tap comes from the next
 // lane, the horizontally interpolated value of the row below is carried to the next iteration.
-//   near[y][x] = kappa * prb[iy][ix] * ((1-rho) h[iy][ix] + rho h[iy+1][ix]),
-//   h[r][c] = (1-gam) psi[R+r][C+c] + gam psi[R+r][C+c+1]        (kernels.cu:95-107; zero outside)
+//   B[y][x] = kappa * ((1-rho) hq[iy][ix] + rho hq[iy+1][ix]),   (iy, ix) = (y - o, x - o)
+//   hq[r][c] = (1-gam) psi[R+r][C+c] + gam psi[R+r][C+c+1]        (kernels.cu:95-107; zero outside)
+// (the probe factor is applied by the FFT warps when they pick the patch up)
 __device__ __forceinline__ void pipe_gather_any(float2* __restrict__ B, int h, const float2* __restrict__ psi_t,
-                                             const float2* __restrict__ prb, const Geo& g, const Pat& p) {
-  constexpr int PB = Pipe::PB, N = Plan7P::N, CH = 8;
+                                                const Geo& g, const Pat& p) {
+  constexpr int PB = Pipe::PB, N = Plan7P::N, CH = 4;
   const int lane = h & 31;
   const int ix = h - g.o;
   const int oc = p.C + ix;
@@ -133,93 +137,72 @@ __device__ __forceinline__ void pipe_gather_any(float2* __restrict__ B, int h, c
   const bool tap0 = ix >= 0 && ix <= g.P && oc < g.n;               // this lane's own object pixel is needed
   const bool tap1 = lane == 31 && ix + 1 <= g.P && ix + 1 >= 0 && oc + 1 < g.n;  // right tap no lane provides
   const float2 z = make_float2(0.f, 0.f);
-  const float a0 = 1.f - p.gam, a1 = p.gam, b0 = 1.f - p.rho, b1 = p.rho;
+  const float a0 = 1.f - p.gam, a1 = p.gam, kb0 = g.kappa * (1.f - p.rho), kb1 = g.kappa * p.rho;
   const float2* col = psi_t + (ptrdiff_t)(p.R - g.o) * g.n + oc;    // + y * n: object pixel of frame row y
-  const float2* pcol = prb + (ptrdiff_t)(-g.o) * g.P + ix;          // + y * P: probe pixel of frame row y
   float2* bcol = B + 1 + h;
-  // h-value of frame row y (object row R + y - o), zero outside the window rows [o, o+P] / the object
-  auto hrow = [&](int y, float2 f0, float2 fx) {
+  auto hrow = [&](float2 f0, float2 fx) {
     float2 f1 = make_float2(__shfl_down_sync(0xffffffffu, f0.x, 1), __shfl_down_sync(0xffffffffu, f0.y, 1));
     if (lane == 31) f1 = fx;
-    (void)y;
     return make_float2(a0 * f0.x + a1 * f1.x, a0 * f0.y + a1 * f1.y);
   };
+  // rows of the window [o, o+P] (the last one only as the lower tap) that lie inside the object
   auto rowok = [&](int y) { return y >= g.o && y <= g.o + g.P && p.R + y - g.o < g.nz; };
   float2 hc;
   {
     const bool ok = rowok(0);
     const float2 f0 = (ok && tap0) ? __ldg(col) : z;
     const float2 fx = (ok && tap1) ? __ldg(col + 1) : z;
-    hc = hrow(0, f0, fx);
+    hc = hrow(f0, fx);
   }
 #pragma unroll 1
   for (int y0 = 0; y0 < N; y0 += CH) {
-    float2 f0[CH], fx[CH], pr[CH];
+    float2 f0[CH], fx[CH];
 #pragma unroll
     for (int j = 0; j < CH; ++j) {
       const int y = y0 + 1 + j;  // tap row of output row y0 + j
       const bool ok = rowok(y);
       f0[j] = (ok && tap0) ? __ldg(col + (ptrdiff_t)y * g.n) : z;
       fx[j] = (ok && tap1) ? __ldg(col + (ptrdiff_t)y * g.n + 1) : z;
-      const int yo = y0 + j;
-      pr[j] = (colv && yo >= g.o && yo < g.o + g.P) ? __ldg(pcol + (ptrdiff_t)yo * g.P) : z;
     }
 #pragma unroll
     for (int j = 0; j < CH; ++j) {
-      const float2 hn = hrow(y0 + 1 + j, f0[j], fx[j]);
-      const float2 t = make_float2(g.kappa * (b0 * hc.x + b1 * hn.x), g.kappa * (b0 * hc.y + b1 * hn.y));
-      bcol[(y0 + j) * PB] = make_float2(pr[j].x * t.x - pr[j].y * t.y, pr[j].x * t.y + pr[j].y * t.x);
+      const int yo = y0 + j;
+      const float2 hn = hrow(f0[j], fx[j]);
+      const bool inw = colv && yo >= g.o && yo < g.o + g.P;
+      bcol[yo * PB] = inw ? make_float2(kb0 * hc.x + kb1 * hn.x, kb0 * hc.y + kb1 * hn.y) : z;
       hc = hn;
     }
   }
 }
 
 // ---------------------------------------------------------------- helpers: scatter out of B
-// B holds near = IFFT2(residual) (frame order).  t = scale * conj(prb) * near; the bilinear spread is
-// separable:  hq[y][x] = (1-gam) t[y][x] + gam t[y][x-1],  out[y][x] = (1-rho) hq[y][x] + rho hq[y-1][x],
+// B holds t = gscale * conj(prb) * IFFT2(residual) (frame order, zero outside the probe window).  The
+// bilinear spread is separable:
+//   hq[y][x] = (1-gam) t[y][x] + gam t[y][x-1],  out[y][x] = (1-rho) hq[y][x] + rho hq[y-1][x],
 // one vector reduction per object pixel (kernels.cu:69-81 issues 8 scalar atomics per probe pixel).
-__device__ __forceinline__ void pipe_scatter_any(const float2* __restrict__ B, int h, const float2* __restrict__ prb,
-                                              float scale, float2* __restrict__ grad_t, const Geo& g,
-                                              const Pat& p) {
-  constexpr int PB = Pipe::PB, N = Plan7P::N, CH = 8;
-  const int lane = h & 31;
+__device__ __forceinline__ void pipe_scatter_any(const float2* __restrict__ B, int h, float2* __restrict__ grad_t,
+                                                 const Geo& g, const Pat& p) {
+  constexpr int PB = Pipe::PB, N = Plan7P::N, CH = 4;
   const int ix = h - g.o;
   const int oc = p.C + ix;
-  const bool colv = (unsigned)ix < (unsigned)g.P;
-  const bool colv_l = (unsigned)(ix - 1) < (unsigned)g.P;            // the column to the left is a probe column
   const bool outc = ix >= 0 && ix <= g.P && oc < g.n;                // this thread's object column exists
   const float2 z = make_float2(0.f, 0.f);
   const float a0 = 1.f - p.gam, a1 = p.gam, b0 = 1.f - p.rho, b1 = p.rho;
   const float2* bcol = B + 1 + h;
-  const float2* pcol = prb + (ptrdiff_t)(-g.o) * g.P + ix;
   float2* dst = grad_t + (ptrdiff_t)(p.R - g.o) * g.n + oc;          // + y * n
-  auto tval = [&](float2 pr, float2 nr) {  // scale * conj(pr) * nr
-    return make_float2(scale * (pr.x * nr.x + pr.y * nr.y), scale * (pr.x * nr.y - pr.y * nr.x));
-  };
   float2 hp = z;
 #pragma unroll 1
   for (int y0 = 0; y0 < N; y0 += CH) {
-    float2 nr[CH], pr[CH], nl[CH], pl[CH];
+    float2 tc[CH], tl[CH];
 #pragma unroll
     for (int j = 0; j < CH; ++j) {
-      const int y = y0 + j;
-      const bool rowv = y >= g.o && y < g.o + g.P;
-      nr[j] = bcol[y * PB];
-      pr[j] = (rowv && colv) ? __ldg(pcol + (ptrdiff_t)y * g.P) : z;
-      nl[j] = z;
-      pl[j] = z;
-      if (lane == 0) {  // the left neighbour belongs to another warp (or is the guard column)
-        nl[j] = bcol[y * PB - 1];
-        pl[j] = (rowv && colv_l) ? __ldg(pcol + (ptrdiff_t)y * g.P - 1) : z;
-      }
+      tc[j] = bcol[(y0 + j) * PB];
+      tl[j] = bcol[(y0 + j) * PB - 1];  // column 0 of B is a guard column of zeros
     }
 #pragma unroll
     for (int j = 0; j < CH; ++j) {
       const int y = y0 + j;
-      const float2 tc = tval(pr[j], nr[j]);
-      float2 tl = make_float2(__shfl_up_sync(0xffffffffu, tc.x, 1), __shfl_up_sync(0xffffffffu, tc.y, 1));
-      if (lane == 0) tl = tval(pl[j], nl[j]);
-      const float2 hq = make_float2(a0 * tc.x + a1 * tl.x, a0 * tc.y + a1 * tl.y);
+      const float2 hq = make_float2(a0 * tc[j].x + a1 * tl[j].x, a0 * tc[j].y + a1 * tl[j].y);
       if (outc && y >= g.o && y <= g.o + g.P && p.R + y - g.o < g.nz)
         atomicAdd(dst + (ptrdiff_t)y * g.n, make_float2(b0 * hq.x + b1 * hp.x, b0 * hq.y + b1 * hp.y));
       hp = hq;
@@ -229,13 +212,12 @@ __device__ __forceinline__ void pipe_scatter_any(const float2* __restrict__ B, i
     if (outc && p.R + g.P < g.nz) atomicAdd(dst + (ptrdiff_t)N * g.n, make_float2(b1 * hp.x, b1 * hp.y));
     if (h < 32 && p.C + g.P < g.n) {  // object column C + P: only the gam * t[.][P-1] share
       const float2* bl = B + N;         // B[y][1 + (N-1)]
-      const float2* pq = prb + (g.P - 1);
       float2* de = grad_t + (ptrdiff_t)p.R * g.n + p.C + g.P;
       for (int y = h; y <= N; y += 32) {
-        const float2 tc = y < N ? tval(__ldg(pq + (ptrdiff_t)y * g.P), bl[y * PB]) : z;
-        const float2 tu = y > 0 ? tval(__ldg(pq + (ptrdiff_t)(y - 1) * g.P), bl[(y - 1) * PB]) : z;
+        const float2 t0 = y < N ? bl[y * PB] : z;
+        const float2 tu = y > 0 ? bl[(y - 1) * PB] : z;
         if (p.R + y < g.nz)
-          atomicAdd(de + (ptrdiff_t)y * g.n, make_float2(a1 * (b0 * tc.x + b1 * tu.x), a1 * (b0 * tc.y + b1 * tu.y)));
+          atomicAdd(de + (ptrdiff_t)y * g.n, make_float2(a1 * (b0 * t0.x + b1 * tu.x), a1 * (b0 * t0.y + b1 * tu.y)));
       }
     }
   }
@@ -244,14 +226,13 @@ __device__ __forceinline__ void pipe_scatter_any(const float2* __restrict__ B, i
 // ---------------------------------------------------------------- helpers: fast paths
 // Full probe window (P == N) lying inside the object: no predicates, pointers advanced row by row.
 __device__ __forceinline__ void pipe_gather_fast(float2* __restrict__ B, int h, const float2* __restrict__ psi_t,
-                                                 const float2* __restrict__ prb, const Geo& g, const Pat& p) {
+                                                 const Geo& g, const Pat& p) {
   constexpr int PB = Pipe::PB, N = Plan7P::N, CH = 8;
   const bool last = (h & 31) == 31;
   const float2 z = make_float2(0.f, 0.f);
   const float a0 = 1.f - p.gam, a1 = p.gam, kb0 = g.kappa * (1.f - p.rho), kb1 = g.kappa * p.rho;
   const int n = g.n;
   const float2* src = psi_t + (size_t)p.R * n + p.C + h;
-  const float2* pp = prb + h;
   float2* bc = B + 1 + h;
   auto hval = [&](float2 f0, float2 fx) {
     float2 f1 = make_float2(__shfl_down_sync(0xffffffffu, f0.x, 1), __shfl_down_sync(0xffffffffu, f0.y, 1));
@@ -266,65 +247,61 @@ __device__ __forceinline__ void pipe_gather_fast(float2* __restrict__ B, int h, 
     hc = hval(f0, fx);
   }
   src += n;
+  // two chunks of loads in flight: the taps of rows y0+CH .. are requested before rows y0 .. are used
+  float2 f0[CH], fx[CH];
+#pragma unroll
+  for (int j = 0; j < CH; ++j) {
+    f0[j] = __ldg(src + j * n);
+    fx[j] = z;
+    if (last) fx[j] = __ldg(src + j * n + 1);
+  }
+  src += CH * n;
 #pragma unroll 1
   for (int y0 = 0; y0 < N; y0 += CH) {
-    float2 f0[CH], fx[CH], pr[CH];
+    float2 g0[CH], gx[CH];
+    if (y0 + CH < N) {
 #pragma unroll
-    for (int j = 0; j < CH; ++j) {
-      f0[j] = __ldg(src + j * n);
-      fx[j] = z;
-      if (last) fx[j] = __ldg(src + j * n + 1);
-      pr[j] = __ldg(pp + j * N);
+      for (int j = 0; j < CH; ++j) {
+        g0[j] = __ldg(src + j * n);
+        gx[j] = z;
+        if (last) gx[j] = __ldg(src + j * n + 1);
+      }
+      src += CH * n;
     }
-    src += CH * n;
-    pp += CH * N;
 #pragma unroll
     for (int j = 0; j < CH; ++j) {
       const float2 hn = hval(f0[j], fx[j]);
-      const float2 t = make_float2(kb0 * hc.x + kb1 * hn.x, kb0 * hc.y + kb1 * hn.y);
-      bc[(y0 + j) * PB] = make_float2(pr[j].x * t.x - pr[j].y * t.y, pr[j].x * t.y + pr[j].y * t.x);
+      bc[(y0 + j) * PB] = make_float2(kb0 * hc.x + kb1 * hn.x, kb0 * hc.y + kb1 * hn.y);
       hc = hn;
+    }
+#pragma unroll
+    for (int j = 0; j < CH; ++j) {
+      f0[j] = g0[j];
+      fx[j] = gx[j];
     }
   }
 }
 
-__device__ __forceinline__ void pipe_scatter_fast(const float2* __restrict__ B, int h,
-                                                  const float2* __restrict__ prb, float scale,
-                                                  float2* __restrict__ grad_t, const Geo& g, const Pat& p) {
+__device__ __forceinline__ void pipe_scatter_fast(const float2* __restrict__ B, int h, float2* __restrict__ grad_t,
+                                                  const Geo& g, const Pat& p) {
   constexpr int PB = Pipe::PB, N = Plan7P::N, CH = 8;
-  const bool first = (h & 31) == 0;
-  const bool hasl = h > 0;
   const float2 z = make_float2(0.f, 0.f);
   const float a0 = 1.f - p.gam, a1 = p.gam, b0 = 1.f - p.rho, b1 = p.rho;
   const int n = g.n;
   const float2* bc = B + 1 + h;
-  const float2* pp = prb + h;
   float2* dst = grad_t + (size_t)p.R * n + p.C + h;
-  auto tval = [&](float2 pr, float2 nr) {  // scale * conj(pr) * nr
-    return make_float2(scale * (pr.x * nr.x + pr.y * nr.y), scale * (pr.x * nr.y - pr.y * nr.x));
-  };
   float2 hp = z;
 #pragma unroll 1
   for (int y0 = 0; y0 < N; y0 += CH) {
-    float2 nr[CH], pr[CH], nl[CH], pl[CH];
+    float2 tc[CH], tl[CH];
 #pragma unroll
     for (int j = 0; j < CH; ++j) {
-      nr[j] = bc[(y0 + j) * PB];
-      pr[j] = __ldg(pp + j * N);
-      nl[j] = z;
-      pl[j] = z;
-      if (first) {  // the left neighbour belongs to another warp (guard column of zeros for h == 0)
-        nl[j] = bc[(y0 + j) * PB - 1];
-        if (hasl) pl[j] = __ldg(pp + j * N - 1);
-      }
+      tc[j] = bc[(y0 + j) * PB];
+      tl[j] = bc[(y0 + j) * PB - 1];  // column 0 of B is a guard column of zeros
     }
-    pp += CH * N;
 #pragma unroll
     for (int j = 0; j < CH; ++j) {
-      const float2 tc = tval(pr[j], nr[j]);
-      float2 tl = make_float2(__shfl_up_sync(0xffffffffu, tc.x, 1), __shfl_up_sync(0xffffffffu, tc.y, 1));
-      if (first) tl = tval(pl[j], nl[j]);
-      const float2 hq = make_float2(a0 * tc.x + a1 * tl.x, a0 * tc.y + a1 * tl.y);
+      const float2 hq = make_float2(a0 * tc[j].x + a1 * tl[j].x, a0 * tc[j].y + a1 * tl[j].y);
       atomicAdd(dst + j * n, make_float2(b0 * hq.x + b1 * hp.x, b0 * hq.y + b1 * hp.y));
       hp = hq;
     }
@@ -333,30 +310,93 @@ __device__ __forceinline__ void pipe_scatter_fast(const float2* __restrict__ B, 
   atomicAdd(dst, make_float2(b1 * hp.x, b1 * hp.y));  // the row below the frame
   if (h < 32) {  // object column C + P: only the gam * t[.][P-1] share
     const float2* bl = B + N;  // B[y][1 + (N-1)]
-    const float2* pq = prb + (N - 1);
     float2* de = grad_t + (size_t)p.R * n + p.C + N;
     for (int y = h; y <= N; y += 32) {
-      const float2 tc = y < N ? tval(__ldg(pq + y * N), bl[y * PB]) : z;
-      const float2 tu = y > 0 ? tval(__ldg(pq + (y - 1) * N), bl[(y - 1) * PB]) : z;
-      atomicAdd(de + (size_t)y * n, make_float2(a1 * (b0 * tc.x + b1 * tu.x), a1 * (b0 * tc.y + b1 * tu.y)));
+      const float2 t0 = y < N ? bl[y * PB] : z;
+      const float2 tu = y > 0 ? bl[(y - 1) * PB] : z;
+      atomicAdd(de + (size_t)y * n, make_float2(a1 * (b0 * t0.x + b1 * tu.x), a1 * (b0 * t0.y + b1 * tu.y)));
     }
   }
 }
 
 __device__ __forceinline__ void pipe_gather(float2* __restrict__ B, int h, const float2* __restrict__ psi_t,
-                                            const float2* __restrict__ prb, const Geo& g, const Pat& p) {
+                                            const Geo& g, const Pat& p) {
   if (g.P == Plan7P::N && p.inside)
-    pipe_gather_fast(B, h, psi_t, prb, g, p);
+    pipe_gather_fast(B, h, psi_t, g, p);
   else
-    pipe_gather_any(B, h, psi_t, prb, g, p);
+    pipe_gather_any(B, h, psi_t, g, p);
 }
-__device__ __forceinline__ void pipe_scatter(const float2* __restrict__ B, int h, const float2* __restrict__ prb,
-                                             float scale, float2* __restrict__ grad_t, const Geo& g,
-                                             const Pat& p) {
+__device__ __forceinline__ void pipe_scatter(const float2* __restrict__ B, int h, float2* __restrict__ grad_t,
+                                             const Geo& g, const Pat& p) {
   if (g.P == Plan7P::N && p.inside)
-    pipe_scatter_fast(B, h, prb, scale, grad_t, g, p);
+    pipe_scatter_fast(B, h, grad_t, g, p);
   else
-    pipe_scatter_any(B, h, prb, scale, grad_t, g, p);
+    pipe_scatter_any(B, h, grad_t, g, p);
+}
+
+// The hand-over pass of the FFT warps over their own 32 positions of B, in place:
+//   out: B <- v   (the previous pattern's gscale * conj(prb) * IFFT2(residual));   in: v <- B (kappa * patch)
+// Eight positions at a time through volatile accesses: an unrestricted schedule hoists all 32 loads and
+// needs old + new values live (128 registers), which puts the whole array into local memory.
+template <bool LOAD>
+__device__ __forceinline__ void pipe_handover(float2 (&v)[32], float2* bp) {
+  using P = Plan7P;
+  const unsigned sb = smem_u32(bp);
+#pragma unroll
+  for (int e0 = 0; e0 < 32; e0 += 8) {
+    float2 t[8];
+    if (LOAD) {
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        int dx, dy;
+        elem_offset<P::S0>(e0 + j, dx, dy);
+        asm volatile("ld.volatile.shared.v2.f32 {%0, %1}, [%2];"
+                     : "=f"(t[j].x), "=f"(t[j].y)
+                     : "r"(sb + (unsigned)(dy * Pipe::PB + dx) * 8u)
+                     : "memory");
+      }
+    }
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      int dx, dy;
+      elem_offset<P::S0>(e0 + j, dx, dy);
+      asm volatile("st.volatile.shared.v2.f32 [%0], {%1, %2};" ::"r"(sb + (unsigned)(dy * Pipe::PB + dx) * 8u),
+                   "f"(v[e0 + j].x), "f"(v[e0 + j].y)
+                   : "memory");
+      if (LOAD) v[e0 + j] = t[j];
+    }
+  }
+}
+// v <- s * prb * v (CONJ = false, kernels.cu:105-106) or s * conj(prb) * v (CONJ = true, kernels.cu:71-72) on
+// the thread's stage-0 positions (the pipelined kernel is only launched for P == N: the probe covers the
+// frame).  Both multiplies of a pattern use that pattern's own probe, read from L2 each time, so that
+// nothing depends on "same angle as the previous pattern?".  The loads are pinned behind a barrier of
+// the FFT warps, eight at a time: ptxas otherwise batches all 32 (64 registers) and spills the spectrum.
+template <bool CONJ>
+__device__ __forceinline__ void pipe_probe_mul(float2 (&v)[32], const float2* __restrict__ pp, float s) {
+  using P = Plan7P;
+#pragma unroll
+  for (int e0 = 0; e0 < 32; e0 += 8) {
+    float2 pr[8];
+    __syncwarp();  // volatile loads stay in program order (ptxas batches .nc loads even across barriers)
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      int dx, dy;
+      elem_offset<P::S0>(e0 + j, dx, dy);
+      asm volatile("ld.volatile.global.v2.f32 {%0, %1}, [%2];"
+                   : "=f"(pr[j].x), "=f"(pr[j].y)
+                   : "l"(pp + dy * P::N + dx)
+                   : "memory");
+    }
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      const float2 w = v[e0 + j];
+      if (CONJ)
+        v[e0 + j] = make_float2(s * (pr[j].x * w.x + pr[j].y * w.y), s * (pr[j].x * w.y - pr[j].y * w.x));
+      else
+        v[e0 + j] = make_float2(pr[j].x * w.x - pr[j].y * w.y, pr[j].x * w.y + pr[j].y * w.x);
+    }
+  }
 }
 
 // ------------------------------------------------------------------------------------------
@@ -382,7 +422,7 @@ __global__ void __launch_bounds__(Pipe::NTHREADS) k_grad_pipe(const PassArgs a,
 
   if (tid < Pipe::NFFT) {
     // ================================================================ FFT warps
-    const float fscale = a.sc[0], iscale = a.sc[1];
+    const float fscale = a.sc[0], iscale = a.sc[1], gscale = a.sc[2] * g.kappa;
     int xf0, yf0, xf2, yf2;
     fixed_coords<P::S0, P::WBITS>(tid, xf0, yf0);
     fixed_coords<P::S2, P::WBITS>(tid, xf2, yf2);
@@ -396,38 +436,11 @@ __global__ void __launch_bounds__(Pipe::NTHREADS) k_grad_pipe(const PassArgs a,
       const Pat p = make_pat(a.scan, pat, g);
       if (p.skip) continue;  // F = 0 -> residual 0 -> no contribution
       nbar_sync(Pipe::BAR_FULL, Pipe::NTHREADS);
-      // near(pat) in, the previous pattern's result out: in place, eight positions at a time through
-      // volatile accesses (ptxas would otherwise hoist all 32 loads: old + new values live = 128
-      // registers, and the whole spectrum array ends up in local memory across the loop).  Before the
-      // first pattern v is zero: what lands in B then is never scattered and is overwritten by the
-      // next gather.
-      {
-        const unsigned sb = smem_u32(bp);
-#pragma unroll
-        for (int e0 = 0; e0 < 32; e0 += 8) {
-          float2 t[8];
-#pragma unroll
-          for (int j = 0; j < 8; ++j) {
-            int dx, dy;
-            elem_offset<P::S0>(e0 + j, dx, dy);
-            asm volatile("ld.volatile.shared.v2.f32 {%0, %1}, [%2];"
-                         : "=f"(t[j].x), "=f"(t[j].y)
-                         : "r"(sb + (unsigned)(dy * Pipe::PB + dx) * 8u)
-                         : "memory");
-          }
-#pragma unroll
-          for (int j = 0; j < 8; ++j) {
-            int dx, dy;
-            elem_offset<P::S0>(e0 + j, dx, dy);
-            asm volatile("st.volatile.shared.v2.f32 [%0], {%1, %2};" ::"r"(sb + (unsigned)(dy * Pipe::PB + dx) * 8u),
-                         "f"(v[e0 + j].x), "f"(v[e0 + j].y)
-                         : "memory");
-            v[e0 + j] = t[j];
-          }
-        }
-      }
+      const float2* prb_in = a.prb + (size_t)(pat / g.S) * a.prb_ts;
+      pipe_handover<true>(v, bp);  // (before the first pattern v is zero)
       __threadfence_block();
       nbar_arrive(Pipe::BAR_SWAPPED, Pipe::NTHREADS);
+      pipe_probe_mul<false>(v, prb_in + yf0 * P::N + xf0, 1.f);
       pipe_fft_forward(v, tile, tw, tid);
       {
         const float* dpat = a.data + (size_t)pat * NN + lbase;
@@ -457,23 +470,18 @@ __global__ void __launch_bounds__(Pipe::NTHREADS) k_grad_pipe(const PassArgs a,
         }
       }
       pipe_fft_inverse(v, tile, tw, tid);
+      pipe_probe_mul<true>(v, prb_in + yf0 * P::N + xf0, gscale);
       have = true;
     }
     if (have) {  // hand the last result over
       nbar_sync(Pipe::BAR_FULL, Pipe::NTHREADS);
-#pragma unroll
-      for (int e = 0; e < 32; ++e) {
-        int dx, dy;
-        elem_offset<P::S0>(e, dx, dy);
-        bp[dy * Pipe::PB + dx] = v[e];
-      }
+      pipe_handover<false>(v, bp);
       __threadfence_block();
       nbar_arrive(Pipe::BAR_SWAPPED, Pipe::NTHREADS);
     }
   } else {
     // ================================================================ helper warps
     const int h = tid - Pipe::NFFT;
-    const float gscale = a.sc[2] * g.kappa;
     auto next_pattern = [&](int pat) {  // first non-skipped pattern of this CTA at or after `pat`
       for (; pat < npat; pat += gridDim.x) {
         const float2 sc = __ldg(a.scan + pat);
@@ -497,7 +505,7 @@ __global__ void __launch_bounds__(Pipe::NTHREADS) k_grad_pipe(const PassArgs a,
     if (cur >= 0) {
       const int t = cur / g.S;
       l2_prefetch(cur);
-      pipe_gather(B, h, a.psi + (size_t)t * g.nz * g.n, a.prb + (size_t)t * a.prb_ts, g, make_pat(a.scan, cur, g));
+      pipe_gather(B, h, a.psi + (size_t)t * g.nz * g.n, g, make_pat(a.scan, cur, g));
       __threadfence_block();
       nbar_arrive(Pipe::BAR_FULL, Pipe::NTHREADS);
     }
@@ -507,13 +515,12 @@ __global__ void __launch_bounds__(Pipe::NTHREADS) k_grad_pipe(const PassArgs a,
       nbar_sync(Pipe::BAR_SWAPPED, Pipe::NTHREADS);  // B: result of `prev`; the FFT warps hold near(cur)
       if (prev >= 0) {
         const int t = prev / g.S;
-        pipe_scatter(B, h, a.prb + (size_t)t * a.prb_ts, gscale, a.grad + (size_t)t * g.nz * g.n, g,
-                     make_pat(a.scan, prev, g));
+        pipe_scatter(B, h, a.grad + (size_t)t * g.nz * g.n, g, make_pat(a.scan, prev, g));
       }
       if (nxt >= 0) {
         const int t = nxt / g.S;
         nbar_sync(4, Pipe::NHELP);  // every helper is done reading B (scatter reads neighbouring columns)
-        pipe_gather(B, h, a.psi + (size_t)t * g.nz * g.n, a.prb + (size_t)t * a.prb_ts, g, make_pat(a.scan, nxt, g));
+        pipe_gather(B, h, a.psi + (size_t)t * g.nz * g.n, g, make_pat(a.scan, nxt, g));
       }
       __threadfence_block();
       nbar_arrive(Pipe::BAR_FULL, Pipe::NTHREADS);
@@ -523,8 +530,7 @@ __global__ void __launch_bounds__(Pipe::NTHREADS) k_grad_pipe(const PassArgs a,
     if (prev >= 0) {
       nbar_sync(Pipe::BAR_SWAPPED, Pipe::NTHREADS);
       const int t = prev / g.S;
-      pipe_scatter(B, h, a.prb + (size_t)t * a.prb_ts, gscale, a.grad + (size_t)t * g.nz * g.n, g,
-                   make_pat(a.scan, prev, g));
+      pipe_scatter(B, h, a.grad + (size_t)t * g.nz * g.n, g, make_pat(a.scan, prev, g));
     }
   }
 }

@@ -269,3 +269,23 @@ def test_cg_full_size_vs_reference(name):
             print("   %s: reference vs f64 %.2e   fused vs f64 %.2e" % (k, e_ref, e_got))
             # factor 3 on a single draw: see tests/test_gpu_cg.py::_assert_parity for the measurements
             assert e_got < max(3 * e_ref, TOL_CG), (k, e_got, e_ref)
+
+
+def test_pipelined_kernel_parity_subprocess():
+    """The opt-in warp-specialised 128^2 object-gradient kernel (PTX_PIPE=1, csrc/ptycho_pipe.cuh): the
+    same full-size gradient check as above (interior, edge and skipped positions, two probe modes so
+    that the multi-mode variant runs too), in a fresh interpreter because the switch is read once."""
+    import os
+    import subprocess
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    code = (
+        "import sys; sys.path[:0] = [%r, %r, %r]\n"
+        "import test_gpu_fullsize as T\n"
+        "T.test_grad_ptycho_batch_full_size(128, 1, 'poisson', 1024, 512, 512)\n"
+        "T.test_grad_ptycho_batch_full_size(128, 2, 'gaussian', 700, 300, 320)\n"
+        "from libtike.cufft.ptychofft import lib\n"
+        "print('PIPE OK')\n" % (root, os.path.join(root, "libtike-cufft_b200"), os.path.join(root, "tests")))
+    p = subprocess.run([sys.executable, "-c", code], env=dict(os.environ, PTX_PIPE="1"), capture_output=True,
+                       text=True, timeout=900)
+    assert p.returncode == 0 and "PIPE OK" in p.stdout, p.stdout[-2000:] + p.stderr[-3000:]
