@@ -25,6 +25,9 @@
  *     SURVEY.md Q12).  Work is enqueued asynchronously; no host sync inside.
  *   - outputs of ptx_adj ACCUMULATE into caller-zeroed arrays, exactly like the
  *     reference's atomics (ptycho.py:102, 118); ptx_fwd overwrites g fully.
+ *   - a plan owns per-CTA scratch (staging frames, accumulators, running sums) that its kernels index
+ *     by blockIdx alone: a plan may be used from ONE stream at a time.  Calls on the same stream are
+ *     ordered by the stream; to overlap work, overlap copies, or create one plan per stream.
  *   - supported detector sizes in this build: ndet in {64, 128, 256, 512}; nprb <= ndet.
  *     Anything else fails loudly with PTX_EUNSUPPORTED (there is no CPU or
  *     library fallback).
