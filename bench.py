@@ -187,6 +187,8 @@ def dist_setup(ngpus):
     local = int(os.environ.get("LOCAL_RANK", "0"))
     if world > 1:
         import torch.distributed as dist
+        from libtike.cufft.dist import bind_to_gpu
+        bind_to_gpu(local)  # host staging next to the GPU it feeds (NUMA), best effort
         torch.cuda.set_device(local)
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     else:

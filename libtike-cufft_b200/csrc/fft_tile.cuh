@@ -42,8 +42,31 @@ static inline float2 make_float2(float a, float b) {
 namespace ptx {
 
 // ---------------------------------------------------------------- complex helpers
+// PTX_F32X2 = 1 (device code, default off): complex add / subtract as ONE packed instruction on the
+// (re, im) register pair (sm_100 FADD2 / FFMA2: __fadd2_rn, __ffma2_rn), bit-identical to the scalar
+// pair (a - b = fma(b, -1, a) is exact).  It removes 20 % of the FP32 instructions of a transform
+// (SASS count) but measured no faster on B200 -- 128^2 fused gradient 0.593 vs 0.582 ms, 256^2 1.590 vs
+// 1.594 ms (profiles/r02i_f32x2.txt): the packed forms buy no issue slots and pin register pairs, which
+// costs spills in the 128-register kernels.  Kept as a switch for the record.
+#ifndef PTX_F32X2
+#define PTX_F32X2 0
+#endif
+#if defined(__CUDA_ARCH__) && PTX_F32X2
+PTX_HD float2 cadd(float2 a, float2 b) { return __fadd2_rn(a, b); }
+PTX_HD float2 csub(float2 a, float2 b) { return __ffma2_rn(b, make_float2(-1.f, -1.f), a); }
+#else
 PTX_HD float2 cadd(float2 a, float2 b) { return make_float2(a.x + b.x, a.y + b.y); }
 PTX_HD float2 csub(float2 a, float2 b) { return make_float2(a.x - b.x, a.y - b.y); }
+#endif
+// a + rot90(d), a - rot90(d) without materialising the rotated pair (it would cost two moves)
+template <bool INV>
+PTX_HD float2 cadd_rot(float2 a, float2 d) {
+  return INV ? make_float2(a.x - d.y, a.y + d.x) : make_float2(a.x + d.y, a.y - d.x);
+}
+template <bool INV>
+PTX_HD float2 csub_rot(float2 a, float2 d) {
+  return INV ? make_float2(a.x + d.y, a.y - d.x) : make_float2(a.x - d.y, a.y + d.x);
+}
 PTX_HD float2 cmul(float2 a, float2 b) {
   return make_float2(a.x * b.x - a.y * b.y, a.x * b.y + a.y * b.x);
 }
@@ -80,11 +103,11 @@ template <bool INV, int STRIDE, int EN>
 struct Dft<4, INV, STRIDE, EN> {
   static PTX_HD void run(float2 (&v)[EN], int base) {
     float2 a0 = v[base], a1 = v[base + STRIDE], a2 = v[base + 2 * STRIDE], a3 = v[base + 3 * STRIDE];
-    float2 t0 = cadd(a0, a2), t1 = csub(a0, a2), t2 = cadd(a1, a3), t3 = rot90<INV>(csub(a1, a3));
+    float2 t0 = cadd(a0, a2), t1 = csub(a0, a2), t2 = cadd(a1, a3), d3 = csub(a1, a3);
     v[base] = cadd(t0, t2);
-    v[base + STRIDE] = cadd(t1, t3);
+    v[base + STRIDE] = cadd_rot<INV>(t1, d3);
     v[base + 2 * STRIDE] = csub(t0, t2);
-    v[base + 3 * STRIDE] = csub(t1, t3);
+    v[base + 3 * STRIDE] = csub_rot<INV>(t1, d3);
   }
 };
 
@@ -96,23 +119,22 @@ struct Dft<8, INV, STRIDE, EN> {
     float2 a4 = v[base + 4 * STRIDE], a5 = v[base + 5 * STRIDE], a6 = v[base + 6 * STRIDE],
            a7 = v[base + 7 * STRIDE];
     // even 4-point: a0 a2 a4 a6 ; odd 4-point: a1 a3 a5 a7
-    float2 e0 = cadd(a0, a4), e1 = csub(a0, a4), e2 = cadd(a2, a6), e3 = rot90<INV>(csub(a2, a6));
-    float2 E0 = cadd(e0, e2), E1 = cadd(e1, e3), E2 = csub(e0, e2), E3 = csub(e1, e3);
-    float2 o0 = cadd(a1, a5), o1 = csub(a1, a5), o2 = cadd(a3, a7), o3 = rot90<INV>(csub(a3, a7));
-    float2 O0 = cadd(o0, o2), O1 = cadd(o1, o3), O2 = csub(o0, o2), O3 = csub(o1, o3);
+    float2 e0 = cadd(a0, a4), e1 = csub(a0, a4), e2 = cadd(a2, a6), e3 = csub(a2, a6);
+    float2 E0 = cadd(e0, e2), E1 = cadd_rot<INV>(e1, e3), E2 = csub(e0, e2), E3 = csub_rot<INV>(e1, e3);
+    float2 o0 = cadd(a1, a5), o1 = csub(a1, a5), o2 = cadd(a3, a7), o3 = csub(a3, a7);
+    float2 O0 = cadd(o0, o2), O1 = cadd_rot<INV>(o1, o3), O2 = csub(o0, o2), O3 = csub_rot<INV>(o1, o3);
     // twiddles W8^k (forward: exp(-i pi k/4); inverse: conjugate)
     // W8^1 = (1 -/+ i) h ; W8^2 = -/+ i ; W8^3 = (-1 -/+ i) h
     float2 T1 = INV ? make_float2((O1.x - O1.y) * h, (O1.x + O1.y) * h)
                     : make_float2((O1.x + O1.y) * h, (O1.y - O1.x) * h);
-    float2 T2 = rot90<INV>(O2);
     float2 T3 = INV ? make_float2((-O3.x - O3.y) * h, (O3.x - O3.y) * h)
                     : make_float2((O3.y - O3.x) * h, (-O3.x - O3.y) * h);
     v[base] = cadd(E0, O0);
     v[base + 4 * STRIDE] = csub(E0, O0);
     v[base + STRIDE] = cadd(E1, T1);
     v[base + 5 * STRIDE] = csub(E1, T1);
-    v[base + 2 * STRIDE] = cadd(E2, T2);
-    v[base + 6 * STRIDE] = csub(E2, T2);
+    v[base + 2 * STRIDE] = cadd_rot<INV>(E2, O2);
+    v[base + 6 * STRIDE] = csub_rot<INV>(E2, O2);
     v[base + 3 * STRIDE] = cadd(E3, T3);
     v[base + 7 * STRIDE] = csub(E3, T3);
   }
@@ -132,11 +154,11 @@ struct Dft<16, INV, STRIDE, EN> {
 #pragma unroll
     for (int m = 0; m < 4; ++m) {
       float2 a0 = t[m], a1 = t[4 + m], a2 = t[8 + m], a3 = t[12 + m];
-      float2 u0 = cadd(a0, a2), u1 = csub(a0, a2), u2 = cadd(a1, a3), u3 = rot90<INV>(csub(a1, a3));
+      float2 u0 = cadd(a0, a2), u1 = csub(a0, a2), u2 = cadd(a1, a3), u3 = csub(a1, a3);
       A[0 * 4 + m] = cadd(u0, u2);
-      A[1 * 4 + m] = cadd(u1, u3);
+      A[1 * 4 + m] = cadd_rot<INV>(u1, u3);
       A[2 * 4 + m] = csub(u0, u2);
-      A[3 * 4 + m] = csub(u1, u3);
+      A[3 * 4 + m] = csub_rot<INV>(u1, u3);
     }
     // twiddles W16^(m*k1), m,k1 in 1..3 : exponents 1,2,3,2,4,6,3,6,9
     const float2 w1 = make_float2(c1, INV ? s1 : -s1);
@@ -157,11 +179,11 @@ struct Dft<16, INV, STRIDE, EN> {
 #pragma unroll
     for (int k1 = 0; k1 < 4; ++k1) {
       float2 a0 = A[k1 * 4 + 0], a1 = A[k1 * 4 + 1], a2 = A[k1 * 4 + 2], a3 = A[k1 * 4 + 3];
-      float2 u0 = cadd(a0, a2), u1 = csub(a0, a2), u2 = cadd(a1, a3), u3 = rot90<INV>(csub(a1, a3));
+      float2 u0 = cadd(a0, a2), u1 = csub(a0, a2), u2 = cadd(a1, a3), u3 = csub(a1, a3);
       v[base + (k1 + 0) * STRIDE] = cadd(u0, u2);
-      v[base + (k1 + 4) * STRIDE] = cadd(u1, u3);
+      v[base + (k1 + 4) * STRIDE] = cadd_rot<INV>(u1, u3);
       v[base + (k1 + 8) * STRIDE] = csub(u0, u2);
-      v[base + (k1 + 12) * STRIDE] = csub(u1, u3);
+      v[base + (k1 + 12) * STRIDE] = csub_rot<INV>(u1, u3);
     }
   }
 };

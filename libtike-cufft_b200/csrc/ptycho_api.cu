@@ -330,8 +330,13 @@ static int launch(ptx_plan* p, int kid, PassArgs& a, cudaStream_t st) {
   // (scatter_gather_impl) with plain loads: no tensor map under any policy
   const bool grad_obj1 = ops->N == 64 && (kid == K_GRAD_GAUSS_OBJ || kid == K_GRAD_POIS_OBJ ||
                                           kid == K_GRADC_GAUSS_OBJ || kid == K_GRADC_POIS_OBJ);
+  // (round 2, profiles/r02h_tma256.txt: at 256^2 the probe-gradient pass gains 22 % and the object pass 1 %
+  // from the prefetched tensor copy, so the multi-tile plans use it for every gradient pass as well)
+  const bool grad_any = kid == K_GRAD_GAUSS_OBJ || kid == K_GRAD_GAUSS_PRB || kid == K_GRAD_POIS_OBJ ||
+                        kid == K_GRAD_POIS_PRB || kid == K_GRADC_GAUSS_OBJ || kid == K_GRADC_GAUSS_PRB ||
+                        kid == K_GRADC_POIS_OBJ || kid == K_GRADC_POIS_PRB;
   const bool want = !grad_obj1 &&
-                    (policy == 2 || (policy == 1 && (ls || inten || (ops->RC > 1 && kid == K_FWD))));
+                    (policy == 2 || (policy == 1 && (ls || inten || (ops->RC > 1 && (kid == K_FWD || grad_any)))));
   if (want && kid != K_NEAR && kid != K_ADJ_OBJ && kid != K_ADJ_PRB && !reg_kernel(kid) && a.psi) {
     const bool two = ls;
     if (make_object_map(p, a.psi, &tm_a) && (!two || make_object_map(p, a.psi_b, &tm_b))) a.use_tma = 1;

@@ -21,7 +21,35 @@ import numpy as np
 import torch
 import torch.distributed as dist
 
-__all__ = ["shard_angles", "run_batch_sharded", "ScalarComm"]
+__all__ = ["shard_angles", "run_batch_sharded", "ScalarComm", "bind_to_gpu"]
+
+
+def bind_to_gpu(local_rank):
+    """Best effort: pin the calling process to the CPU cores (hence, by first touch, the host memory)
+    next to GPU `local_rank` -- with one process per GPU the pinned staging buffers and the copies they
+    feed otherwise all hang off one NUMA node.  Returns the affinity mask applied, or None (no NVML,
+    cores outside the container's cpuset, ...); never raises."""
+    try:
+        import os
+        import pynvml
+        pynvml.nvmlInit()
+        vis = os.environ.get("CUDA_VISIBLE_DEVICES")
+        index = int(vis.split(",")[local_rank]) if vis else local_rank
+        handle = pynvml.nvmlDeviceGetHandleByIndex(index)
+        want = set()
+        words = pynvml.nvmlDeviceGetCpuAffinity(handle, (os.cpu_count() + 63) // 64 + 1)
+        for w, bits in enumerate(words):
+            for b in range(64):
+                if bits >> b & 1:
+                    want.add(64 * w + b)
+        allowed = os.sched_getaffinity(0)
+        mask = want & allowed
+        if mask and mask != allowed:
+            os.sched_setaffinity(0, mask)
+            return sorted(mask)
+    except Exception:
+        pass
+    return None
 
 
 def shard_angles(ntheta, world, rank):
