@@ -317,6 +317,15 @@ static int launch(ptx_plan* p, int kid, PassArgs& a, cudaStream_t st) {
   memset(&tm_a, 0, sizeof(tm_a));
   memset(&tm_b, 0, sizeof(tm_b));
   a.use_tma = 0;
+  // column-strip gather through the shared tile (ptycho_device.cuh: gather_strip).  Measured on B200
+  // (profiles/r02l_strip_gather.txt): 64^2 fwd +43 %, fused gradient +6 % (object) / +13 % (probe); 128^2
+  // -4 % ... +1 % (there the extra pass through the 128 KB tile eats what the cheaper loads save), so by
+  // default only the 64^2 plan uses it.  PTX_STRIP=0 / 1 force it off / on for every single-tile plan.
+  static const int strip = []() {
+    const char* e = getenv("PTX_STRIP");
+    return !e ? -1 : !strcmp(e, "0") ? 0 : 1;
+  }();
+  a.strip = strip < 0 ? (ops->N == 64) : strip;
   // PTX_TMA_GATHER = sel (default: where the prefetched tensor copy measured faster than strided
   // loads -- intensity and line-search passes, and the forward operator of the multi-block plans;
   // profiles/) | all | off
@@ -324,7 +333,8 @@ static int launch(ptx_plan* p, int kid, PassArgs& a, cudaStream_t st) {
     const char* e = getenv("PTX_TMA_GATHER");
     return !e ? 1 : !strcmp(e, "off") ? 0 : !strcmp(e, "all") ? 2 : 1;
   }();
-  const bool ls = (kid == K_LS_GAUSS || kid == K_LS_POIS || kid == K_LSAB_GAUSS || kid == K_LSAB_POIS);
+  const bool ls = (kid == K_LS_GAUSS || kid == K_LS_POIS || kid == K_LSAB_GAUSS || kid == K_LSAB_POIS ||
+                   kid == K_LSC_GAUSS || kid == K_LSC_POIS || kid == K_LSCAB_GAUSS || kid == K_LSCAB_POIS);
   const bool inten = (kid == K_INT_GAUSS || kid == K_INT_POIS);
   // the object-gradient pass of the 64^2 plan gathers the NEXT pattern inside its scatter loop
   // (scatter_gather_impl) with plain loads: no tensor map under any policy
@@ -669,8 +679,10 @@ int ptx_cg_linesearch(ptx_plan* p, const void* obj_a, const void* prb_a, int nmo
   a.ncand = ncand;
   a.red = cost;
   cudaStream_t st = (cudaStream_t)stream;
-  if (model == PTX_MODEL_GAUSSIAN) return launch(p, want_ab ? K_LSAB_GAUSS : K_LS_GAUSS, a, st);
-  if (model == PTX_MODEL_POISSON) return launch(p, want_ab ? K_LSAB_POIS : K_LS_POIS, a, st);
+  if (model == PTX_MODEL_GAUSSIAN)
+    return launch(p, far_a ? (want_ab ? K_LSCAB_GAUSS : K_LSC_GAUSS) : (want_ab ? K_LSAB_GAUSS : K_LS_GAUSS), a, st);
+  if (model == PTX_MODEL_POISSON)
+    return launch(p, far_a ? (want_ab ? K_LSCAB_POIS : K_LSC_POIS) : (want_ab ? K_LSAB_POIS : K_LS_POIS), a, st);
   return fail(PTX_EINVAL, "unknown model %d", model);
 }
 

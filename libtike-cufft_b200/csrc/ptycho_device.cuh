@@ -105,6 +105,7 @@ struct Cta {
   float2* stash;       // global thread-private scratch, N*N complex: [(k*E + e)*NT + tid]
   float* accp;         // global thread-private scratch, 3*N*N floats
   int tid, xf0, yf0, xf2, yf2;
+  bool strip;          // the tile is free whenever a gather starts: the column-strip gather may use it
   int sbase;           // spec_index of the thread's stage-2 coordinates (element part is immediate)
   int lbase;           // same within one sub-tile's data buffer: fy_local * N + fx
 };
@@ -235,12 +236,80 @@ __device__ __forceinline__ void gather_impl(float2 (&v)[P::E], const Cta<P>& c, 
     v[e] = r;
   }
 }
+// Single-tile plans, full probe window inside the object: the near plane is produced by COLUMN
+// STRIPS and handed to stage-0 ownership through the (free) shared tile.  Thread t owns frame column
+// x = t % N over a run of N*N/NT rows: one coalesced load per object pixel (a warp reads 32 adjacent
+// columns of one object row), the right tap comes from the next lane, the horizontally interpolated
+// value of the row below is carried in a register -- 1.03 global loads per pixel instead of four
+// unaligned 8-byte taps (3.5 wavefronts each; ncu, profiles/r02k_grad128_ncu.txt: the tap gather was
+// 20 % of the fused kernel, bound by L2 latency and LSU queueing).  Costs one extra pass through the
+// tile (store by strips, barrier, load by stage-0 ownership): 2 k wavefronts against 5.5 k saved.
+template <class P>
+__device__ __forceinline__ void gather_strip(float2 (&v)[P::E], const Cta<P>& c,
+                                             const float2* __restrict__ psi_t,
+                                             const float2* __restrict__ prb, const Geo& g,
+                                             const Pat& p) {
+  static_assert(P::RC == 1, "single-tile plans only");
+  constexpr int N = P::N, RUN = N * N / P::NT, CH = 8;
+  static_assert(RUN % CH == 0 && N % 32 == 0, "strip geometry");
+  const int x = c.tid % N, r0 = (c.tid / N) * RUN;
+  const bool last = (c.tid & 31) == 31;
+  const float2 z = make_float2(0.f, 0.f);
+  const float a0 = 1.f - p.gam, a1 = p.gam, kb0 = g.kappa * (1.f - p.rho), kb1 = g.kappa * p.rho;
+  const int n = g.n;
+  const float2* src = psi_t + (size_t)(p.R + r0) * n + p.C + x;
+  const float2* pp = prb + r0 * N + x;
+  float2* tp = c.tile + TileGeom<P>::idx(r0, x);  // + j * RS per row
+  auto hval = [&](float2 f0, float2 fx) {
+    float2 f1 = make_float2(__shfl_down_sync(0xffffffffu, f0.x, 1), __shfl_down_sync(0xffffffffu, f0.y, 1));
+    if (last) f1 = fx;
+    return make_float2(a0 * f0.x + a1 * f1.x, a0 * f0.y + a1 * f1.y);
+  };
+  float2 hc;
+  {
+    const float2 f0 = __ldg(src);
+    float2 fx = z;
+    if (last) fx = __ldg(src + 1);
+    hc = hval(f0, fx);
+  }
+  src += n;
+  __syncthreads();  // the previous user of the tile (an inverse stage, a probe pass) is done reading it
+#pragma unroll 1
+  for (int j0 = 0; j0 < RUN; j0 += CH) {
+    float2 f0[CH], fx[CH], pr[CH];
+#pragma unroll
+    for (int j = 0; j < CH; ++j) {
+      f0[j] = __ldg(src + j * n);
+      fx[j] = z;
+      if (last) fx[j] = __ldg(src + j * n + 1);
+      pr[j] = __ldg(pp + j * N);
+    }
+    src += CH * n;
+    pp += CH * N;
+#pragma unroll
+    for (int j = 0; j < CH; ++j) {
+      const float2 hn = hval(f0[j], fx[j]);
+      const float2 t = make_float2(kb0 * hc.x + kb1 * hn.x, kb0 * hc.y + kb1 * hn.y);
+      tp[(j0 + j) * TileGeom<P>::RS] = make_float2(pr[j].x * t.x - pr[j].y * t.y, pr[j].x * t.y + pr[j].y * t.x);
+      hc = hn;
+    }
+  }
+  __syncthreads();
+  stage_load<typename P::S0, P>(v, c.tile, c.xf0, c.yf0);
+  // stage 0 stores to the positions this thread just loaded: no barrier needed before fft_forward
+}
 template <class P>
 __device__ __forceinline__ void gather_nat(float2 (&v)[P::E], const Cta<P>& c, int cb,
                                            const float2* __restrict__ psi_t,
                                            const float2* __restrict__ prb, const Geo& g,
                                            const Pat& p) {
   if (g.P == P::N) {  // block-uniform
+    if constexpr (P::RC == 1) {
+      if (p.inside && c.strip) {
+        gather_strip<P>(v, c, psi_t, prb, g, p);
+        return;
+      }
+    }
     if (p.inside)
       gather_impl<P, true, true>(v, c, cb, psi_t, prb, g, p);
     else

@@ -46,6 +46,7 @@ struct PassArgs {
   double* red;
   int nmodes, npairs, c0, ncand;
   int use_tma;  // object patches arrive by TMA tensor copies (tensor maps are valid)
+  int strip;    // single-tile plans: column-strip gather through the shared tile (ptycho_device.cuh)
   // position correction (ptycho_register.cuh)
   const double2* reg_E;  // [REG_EROWS][N] table W^(j k), W = exp(2 pi i / (uf N))
   double* reg_out;       // [npat][2] shifts (row, col)
@@ -61,6 +62,7 @@ enum KernelId {
   K_REG_OBJ, K_REG_FOURIER, K_REG_REAL,
   K_GRADC_GAUSS_OBJ, K_GRADC_GAUSS_PRB, K_GRADC_POIS_OBJ, K_GRADC_POIS_PRB,  // + far-field cache output
   K_LSAB_GAUSS, K_LSAB_POIS,  // + the next iteration's a, b sums of every candidate
+  K_LSC_GAUSS, K_LSC_POIS, K_LSCAB_GAUSS, K_LSCAB_POIS,  // first far field read from the gradient pass's cache
   // warp-specialised, pipelined object-gradient kernels (ptycho_pipe.cuh; 128^2 plan only, else null)
   K_PIPE_GAUSS, K_PIPEC_GAUSS, K_PIPE_POIS, K_PIPEC_POIS,      // I = |F|^2 (one mode)
   K_PIPEM_GAUSS, K_PIPEMC_GAUSS, K_PIPEM_POIS, K_PIPEMC_POIS,  // I = the summed intensity map (several modes)

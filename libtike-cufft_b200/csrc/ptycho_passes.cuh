@@ -40,6 +40,7 @@ struct Scratch {  // per-CTA global scratch; every kind is its own contiguous [g
 template <class P>
 __device__ __forceinline__ void cta_setup(Cta<P>& c, unsigned char* raw, const PassArgs& a) {
   c.tid = threadIdx.x;
+  c.strip = a.strip != 0;
   c.tile = reinterpret_cast<float2*>(raw);
   float2* tw = reinterpret_cast<float2*>(raw + Smem<P>::OFF_TW);
   c.dbuf = reinterpret_cast<float*>(raw + Smem<P>::OFF_DBUF);
@@ -498,7 +499,7 @@ __global__ void __launch_bounds__(P::NT) k_grad(const PassArgs a, const __grid_c
 //   ptycho.py:383-393 (object), 451-461 (probe), 253-281 (line_search_sqr)
 // The first far field of a pair is parked in thread-private scratch while the second is transformed.
 // ------------------------------------------------------------------------------------------
-template <class P, int MODEL, bool AB>
+template <class P, int MODEL, bool AB, bool CACHED>
 __global__ void __launch_bounds__(P::NT) k_linesearch(const PassArgs a,
                                                       const __grid_constant__ CUtensorMap tm_a,
                                                       const __grid_constant__ CUtensorMap tm_b) {
@@ -524,8 +525,8 @@ __global__ void __launch_bounds__(P::NT) k_linesearch(const PassArgs a,
       const bool first = (j == 0), last = (j + 1 == a.npairs);
       // the pair's first far field was left in HBM by the gradient pass that preceded this search
       // (reading 8 N^2 bytes costs a quarter of recomputing gather + transform)
-      const float2* t1c = a.far_in ? a.far_in + (size_t)j * a.far_ms + (size_t)pat * NN : nullptr;
-      if (!t1c)
+      const float2* t1c = CACHED ? a.far_in + (size_t)j * a.far_ms + (size_t)pat * NN : nullptr;
+      if constexpr (!CACHED)
         spectrum_pass<P>(
             c, p.skip, [&](int cb, float2(&v)[P::E]) {
               gather_any<P>(v, c, cb, a.use_tma, &tm_a, 2 * pat, t, psi_a, prb_a, g, p);
@@ -540,7 +541,7 @@ __global__ void __launch_bounds__(P::NT) k_linesearch(const PassArgs a,
             });
       spectrum_pass<P>(
           c, p.skip, [&](int cb, float2(&v)[P::E]) {
-            if (t1c && cb == 0 && !p.skip && (c.tid & 15) == 0) {
+            if (CACHED && cb == 0 && !p.skip && (c.tid & 15) == 0) {
               // pull the cached far field from HBM into L2 meanwhile: a warp's register e covers two
               // 128-byte lines (32 lanes x 8 B), one prefetch per line
               for (int k1 = 0; k1 < P::RC; ++k1)
@@ -559,7 +560,7 @@ __global__ void __launch_bounds__(P::NT) k_linesearch(const PassArgs a,
             for (int q = 0; q < 5; ++q) cost[q] = 0.f;
 #pragma unroll
             for (int q = 0; q < (AB ? 10 : 1); ++q) sab[q] = 0.f;
-            const float2* t1p = (t1c && !p.skip) ? t1c + c.sbase + k1 * P::N : nullptr;
+            const float2* t1p = (CACHED && !p.skip) ? t1c + c.sbase + k1 * P::N : nullptr;
             if (last) dp_wait<P>(c);
             // the first far field comes from L2 / HBM: its loads are issued CH at a time ahead of
             // the arithmetic that consumes them (one exposed round trip per CH pixels, not per pixel)
@@ -570,11 +571,18 @@ __global__ void __launch_bounds__(P::NT) k_linesearch(const PassArgs a,
 #pragma unroll
               for (int j = 0; j < CH; ++j) {
                 const int e = e0 + j;
-                if (t1c) {  // block-uniform
+                if (CACHED) {
                   int dx, dy;
                   elem_offset<typename P::S2>(e, dx, dy);
-                  t1v[j] = t1p ? __ldcs(t1p + (P::RC * pos_to_freq_y<P>(dy) * P::N + pos_to_freq_x<P>(dx)))
-                               : make_float2(0.f, 0.f);
+                  // volatile: ptxas otherwise batches all 32 loads ahead of the arithmetic (64 live
+                  // registers) and spills the spectrum -- 576 B of stack per thread in round 1, the
+                  // "unexplained" DRAM writes of profiles/r01m_all128_ncu.txt were that local traffic
+                  t1v[j] = make_float2(0.f, 0.f);
+                  if (t1p)
+                    asm volatile("ld.volatile.global.v2.f32 {%0, %1}, [%2];"
+                                 : "=f"(t1v[j].x), "=f"(t1v[j].y)
+                                 : "l"(t1p + (P::RC * pos_to_freq_y<P>(dy) * P::N + pos_to_freq_x<P>(dx)))
+                                 : "memory");
                 } else {
                   t1v[j] = st[e * P::NT];
                 }
@@ -637,7 +645,7 @@ __global__ void __launch_bounds__(P::NT) k_linesearch(const PassArgs a,
             if (last) dp_next<P>(c, a.data, pat, k1, npat);
             if (k1 == P::RC - 1) {  // next pair of this pattern, or the next pattern
               const int np = last ? pat + (int)gridDim.x : pat;
-              if (a.far_in)  // only second objects are gathered
+              if (CACHED)  // only second objects are gathered
                 patch_prefetch<P>(c, a.use_tma, &tm_b, 2 * np + 1, np, npat, a.scan, g);
               else
                 patch_prefetch<P>(c, a.use_tma, &tm_a, 2 * np, np, npat, a.scan, g);

@@ -61,10 +61,14 @@ void fill_ops_grad(PlanOps& ops) {
 
 template <class P>
 void fill_ops_search(PlanOps& ops) {
-  PTX_SET(K_LS_GAUSS, k_linesearch<P, 0, false>)
-  PTX_SET(K_LS_POIS, k_linesearch<P, 1, false>)
-  PTX_SET(K_LSAB_GAUSS, k_linesearch<P, 0, true>)
-  PTX_SET(K_LSAB_POIS, k_linesearch<P, 1, true>)
+  PTX_SET(K_LS_GAUSS, k_linesearch<P, 0, false, false>)
+  PTX_SET(K_LS_POIS, k_linesearch<P, 1, false, false>)
+  PTX_SET(K_LSAB_GAUSS, k_linesearch<P, 0, true, false>)
+  PTX_SET(K_LSAB_POIS, k_linesearch<P, 1, true, false>)
+  PTX_SET(K_LSC_GAUSS, k_linesearch<P, 0, false, true>)
+  PTX_SET(K_LSC_POIS, k_linesearch<P, 1, false, true>)
+  PTX_SET(K_LSCAB_GAUSS, k_linesearch<P, 0, true, true>)
+  PTX_SET(K_LSCAB_POIS, k_linesearch<P, 1, true, true>)
   PTX_SET(K_REG_OBJ, k_register<P, 0>)
   PTX_SET(K_REG_FOURIER, k_register<P, 1>)
   PTX_SET(K_REG_REAL, k_register<P, 2>)
