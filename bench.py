@@ -489,7 +489,7 @@ def run_b200(args, world, rank, local):
 
     # ---- CG iterations/s
     cg = None
-    if rank == 0:
+    if rank == 0 and not args.no_cg:
         cg = cg_rates(pt, w, data[:1].contiguous(), psi[:1].contiguous(), scan[:1].contiguous(),
                       probe[:1].contiguous())
         cg["config"] = "one %s angle, device resident" % args.workload
@@ -498,6 +498,7 @@ def run_b200(args, world, rank, local):
         coupled = coupled_cg(pt, w, data, psi, scan, probe, world)
         check = scalarcomm_check(pt, world, rank)
         if rank == 0:
+            cg = cg or {}
             cg["coupled"] = coupled
             cg["scalarcomm_check"] = check
     del data, grad, psi

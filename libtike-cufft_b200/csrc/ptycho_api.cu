@@ -233,6 +233,10 @@ static int plan_init(ptx_plan* p) {
   if (per_sm < 1)
     return fail(PTX_ECUDA, "kernel does not fit on an SM (smem %zu B)", ops->smem_bytes);
   p->grid = p->num_sms * per_sm;
+  if (const char* e = getenv("PTX_GRID")) {  // experiment: cap the persistent grid (L2 footprint of the frames)
+    const int cap = atoi(e);
+    if (cap > 0 && cap < p->grid) p->grid = cap;
+  }
   const size_t npat = p->ptheta * p->nscan;
   if ((size_t)p->grid > npat) p->grid = (int)npat;
   CUDA_TRY(cudaMalloc(&p->slots, ops->slots_per_cta * p->grid * sizeof(double)));

@@ -454,45 +454,80 @@ __device__ __forceinline__ void fft_inverse(float2 (&v)[P::E], float2* tile, con
   stage_compute<typename P::S0, true>(v, xf, yf, tw + TL::X0, tw + TL::Y0);
 }
 
+// Frame accesses: L2-only (.cg); -DPTX_FRAME_HINT=1 adds an L2 evict_last cache hint (measured: no effect on DRAM bytes
+// or time at full c4 size, profiles/r02p_frame_hint.txt, so off) -- the frame is
+// the one thing in this kernel that IS re-used from L2 (written and read back twice per pattern) while
+// 260 KB of measured data stream past it per pattern (evict_first, dp_issue).
+#ifndef PTX_FRAME_HINT
+#define PTX_FRAME_HINT 0
+#endif
+__device__ __forceinline__ unsigned long long frame_policy() {
+  unsigned long long pol;
+  asm volatile("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(pol));
+  return pol;
+}
+__device__ __forceinline__ float2 frame_ld(const float2* p, unsigned long long pol) {
+#if PTX_FRAME_HINT
+  float2 r;
+  asm volatile("ld.global.cg.L2::cache_hint.v2.f32 {%0, %1}, [%2], %3;" : "=f"(r.x), "=f"(r.y) : "l"(p), "l"(pol));
+  return r;
+#else
+  (void)pol;
+  return __ldcg(p);
+#endif
+}
+__device__ __forceinline__ void frame_st(float2* p, float2 v, unsigned long long pol) {
+#if PTX_FRAME_HINT
+  asm volatile("st.global.cg.L2::cache_hint.v2.f32 [%0], {%1, %2}, %3;" ::"l"(p), "f"(v.x), "f"(v.y), "l"(pol) : "memory");
+#else
+  (void)pol;
+  __stcg(p, v);
+#endif
+}
+
 // stage-0 ownership <-> scratch frame sub-tile k1 (L2-only accesses: written and read by
 // different threads of the same CTA with a block barrier in between)
 template <class P>
 __device__ __forceinline__ void frame_load_s0(float2 (&v)[P::E], const Cta<P>& c, int k1) {
   const float2* f = c.frame + (size_t)k1 * P::NX * P::NY;
+  const unsigned long long pol = frame_policy();
 #pragma unroll
   for (int e = 0; e < P::E; ++e) {
     int dx, dy;
     elem_offset<typename P::S0>(e, dx, dy);
-    v[e] = __ldcg(f + (c.yf0 | dy) * P::NX + (c.xf0 | dx));
+    v[e] = frame_ld(f + (c.yf0 | dy) * P::NX + (c.xf0 | dx), pol);
   }
 }
 template <class P>
 __device__ __forceinline__ void frame_store_s0(const float2 (&v)[P::E], const Cta<P>& c, int k1) {
   float2* f = c.frame + (size_t)k1 * P::NX * P::NY;
+  const unsigned long long pol = frame_policy();
 #pragma unroll
   for (int e = 0; e < P::E; ++e) {
     int dx, dy;
     elem_offset<typename P::S0>(e, dx, dy);
-    __stcg(f + (c.yf0 | dy) * P::NX + (c.xf0 | dx), v[e]);
+    frame_st(f + (c.yf0 | dy) * P::NX + (c.xf0 | dx), v[e], pol);
   }
 }
 // cross (natural) ownership of block cb <-> scratch frame: register j + RC*b <-> sub-tile j
 template <class P>
 __device__ __forceinline__ void frame_load_cross(float2 (&v)[P::E], const Cta<P>& c, int cb) {
+  const unsigned long long pol = frame_policy();
 #pragma unroll
   for (int e = 0; e < P::E; ++e) {
     int ylow, xc;
     Cross<P>::pair(c.tid, e / P::RC, ylow, xc);
-    v[e] = __ldcg(c.frame + scratch_index<P>(e % P::RC, ylow, cb * Cross<P>::CW + xc));
+    v[e] = frame_ld(c.frame + scratch_index<P>(e % P::RC, ylow, cb * Cross<P>::CW + xc), pol);
   }
 }
 template <class P>
 __device__ __forceinline__ void frame_store_cross(const float2 (&v)[P::E], const Cta<P>& c, int cb) {
+  const unsigned long long pol = frame_policy();
 #pragma unroll
   for (int e = 0; e < P::E; ++e) {
     int ylow, xc;
     Cross<P>::pair(c.tid, e / P::RC, ylow, xc);
-    __stcg(c.frame + scratch_index<P>(e % P::RC, ylow, cb * Cross<P>::CW + xc), v[e]);
+    frame_st(c.frame + scratch_index<P>(e % P::RC, ylow, cb * Cross<P>::CW + xc), v[e], pol);
   }
 }
 
