@@ -186,14 +186,24 @@ int ptx_prepare_data(const float* raw, const long long* ids, size_t nsel, size_t
 /* red[0] += sum |g|^2 ; red[1..2] += sum conj(d) * (g - g0)   (ptycho.py:369-371, 447-449) */
 int ptx_vec_dai_yuan_reduce(const void* g, const void* g0, const void* d, size_t n, double* red,
                             void* stream);
-/* first: d = -g ; else d = -g + (red[0] / (red[1] + i red[2])) * d ; always g0 = g
- * (ptycho.py:366-372, 444-450; the complex beta of Q3 is reproduced) */
-int ptx_vec_dai_yuan_update(const void* g, void* g0, void* d, size_t n, const double* red,
+/* first & 1: d = -g ; else d = -g + (red[0] / (red[1] + i red[2])) * d ; always g0 = g
+ * (ptycho.py:366-372, 444-450; the complex beta of Q3 is reproduced).  first & 2: g is zeroed once it has
+ * been consumed, ready for the next gradient pass to accumulate into (no separate fill launch). */
+int ptx_vec_dai_yuan_update(void* g, void* g0, void* d, size_t n, const double* red,
                             int first, void* stream);
 /* y += (*alpha) * x   (ptycho.py:405, 463) */
 int ptx_vec_axpy(void* y, const void* x, size_t n, const float* alpha_dev, void* stream);
 /* y += alpha * x, alpha passed by value (no device scalar to stage) */
 int ptx_vec_axpy_s(void* y, const void* x, size_t n, float alpha, void* stream);
+/* out = y + alpha * x   (psi + gammapsi * dpsi, ptycho.py:400 / 405, out of place) */
+int ptx_vec_axpy_out(void* out, const void* y, const void* x, size_t n, float alpha, void* stream);
+/* nbytes of x := 0 on the stream (cudaMemsetAsync; the accumulate-into outputs and the packed scalars) */
+int ptx_vec_zero(void* x, size_t nbytes, void* stream);
+/* scan[0, :] += shifts (ptycho.py:403): nscan (row, col) float32 pairs += float64, cast like CuPy's in-place add */
+int ptx_cg_apply_shifts(float* scan, const double* shifts, size_t nscan, void* stream);
+/* dst[0..2] = src[i0], src[i1], src[i2]: a, b and cost of the accepted line-search candidate become the
+ * sums the next iteration opens with (ptycho.py:342-343), without a host round trip */
+int ptx_cg_pick3(double* dst, const double* src, int i0, int i1, int i2, void* stream);
 /* CG scalars on the device, in the reference's float32 arithmetic (ptycho.py:342-351):
  *   red = {a, b} (doubles)  ->  *s_out = a/b ; sc[0] = fscale = b/a (gaussian) or 1 ; sc[1] = (a/b)^2 */
 int ptx_cg_prep_scale(const double* red, int model, float* s_out, float* sc, void* stream);

@@ -40,8 +40,10 @@ __global__ void k_dy_reduce(const float2* __restrict__ gr, const float2* __restr
   block_reduce_add<3, 8>(acc, red, out, threadIdx.x);
 }
 
-__global__ void k_dy_update(const float2* __restrict__ gr, float2* __restrict__ g0,
-                            float2* __restrict__ d, size_t n, const double* red, int first) {
+__global__ void k_dy_update(float2* __restrict__ gr, float2* __restrict__ g0,
+                            float2* __restrict__ d, size_t n, const double* red, int flags) {
+  const int first = flags & 1;
+  const bool zero_g = (flags & 2) != 0;  // the gradient is consumed here: leave it zeroed for the next pass
   float2 beta = make_float2(0.f, 0.f);
   if (!first) {
     // beta = ||g||^2 / (sum conj(d)(g-g0)) : a real divided by a complex (ptycho.py:369-371)
@@ -60,6 +62,34 @@ __global__ void k_dy_update(const float2* __restrict__ gr, float2* __restrict__ 
     }
     d[i] = r;
     g0[i] = a;
+    if (zero_g) gr[i] = make_float2(0.f, 0.f);
+  }
+}
+
+// out = y + alpha * x   (psi + gamma dpsi of the position-correction block, ptycho.py:400)
+__global__ void k_axpy_out(float2* __restrict__ out, const float2* __restrict__ y, const float2* __restrict__ x,
+                           size_t n, float al) {
+  for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n;
+       i += (size_t)gridDim.x * blockDim.x) {
+    const float2 a = y[i], b = x[i];
+    out[i] = make_float2(a.x + al * b.x, a.y + al * b.y);
+  }
+}
+
+// scan[0, :] += shifts: float32 += float64 the way CuPy casts it (ptycho.py:403)
+__global__ void k_apply_shifts(float* __restrict__ scan, const double* __restrict__ shifts, size_t n) {
+  for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n;
+       i += (size_t)gridDim.x * blockDim.x)
+    scan[i] = (float)((double)scan[i] + shifts[i]);
+}
+
+// dst[k] = src[idx[k]], k < 3: hands the a, b, cost of an accepted line-search candidate to the next
+// iteration without a host round trip
+__global__ void k_pick3(double* __restrict__ dst, const double* __restrict__ src, int i0, int i1, int i2) {
+  if (threadIdx.x == 0) {
+    dst[0] = src[i0];
+    dst[1] = src[i1];
+    dst[2] = src[i2];
   }
 }
 
@@ -192,6 +222,14 @@ struct ptx_plan {
   float2* stash;
   float* accp;
   double* slots;
+  // tensor maps of the object arrays seen lately (the CG loop alternates between a handful of pointers;
+  // encoding costs a driver call per launch otherwise)
+  struct TmEntry {
+    const void* ptr;
+    bool ok;
+    CUtensorMap tm;
+  } tmc[6];
+  int tmc_next;
   size_t l2_window;  // bytes of `frame` covered by the persisting-L2 access-policy window (0: none)
   float l2_hit;      // hit ratio of that window (set-aside / window)
   Geo geo;
@@ -299,7 +337,21 @@ static EncodeTiledFn encode_fn() {
   }();
   return fn;
 }
-static bool make_object_map(const ptx_plan* p, const void* psi, CUtensorMap* tm) {
+static bool encode_object_map(const ptx_plan* p, const void* psi, CUtensorMap* tm);
+static bool make_object_map(ptx_plan* p, const void* psi, CUtensorMap* tm) {
+  for (auto& e : p->tmc)
+    if (e.ptr == psi && psi) {
+      if (e.ok) *tm = e.tm;
+      return e.ok;
+    }
+  auto& e = p->tmc[p->tmc_next];
+  p->tmc_next = (p->tmc_next + 1) % 6;
+  e.ptr = psi;
+  e.ok = encode_object_map(p, psi, &e.tm);
+  if (e.ok) *tm = e.tm;
+  return e.ok;
+}
+static bool encode_object_map(const ptx_plan* p, const void* psi, CUtensorMap* tm) {
   const PlanOps* ops = p->ops;
   if (!ops->patch_w || !psi || ((uintptr_t)psi & 15) || (p->n & 1) || !encode_fn()) return false;
   const cuuint64_t dims[3] = {p->n, p->nz, p->ptheta};
@@ -351,8 +403,10 @@ static int launch(ptx_plan* p, int kid, PassArgs& a, cudaStream_t st) {
                         kid == K_GRADC_POIS_OBJ || kid == K_GRADC_POIS_PRB;
   const bool want = !grad_obj1 &&
                     (policy == 2 || (policy == 1 && (ls || inten || (ops->RC > 1 && (kid == K_FWD || grad_any)))));
-  if (want && kid != K_NEAR && kid != K_ADJ_OBJ && kid != K_ADJ_PRB && !reg_kernel(kid) && a.psi) {
-    const bool two = ls;
+  const bool reg_tma = kid == K_REG_OBJ && ops->RC > 1 && policy != 0;  // position correction, N > 128
+  if ((want || reg_tma) && kid != K_NEAR && kid != K_ADJ_OBJ && kid != K_ADJ_PRB &&
+      (!reg_kernel(kid) || reg_tma) && a.psi) {
+    const bool two = ls || reg_tma;
     if (make_object_map(p, a.psi, &tm_a) && (!two || make_object_map(p, a.psi_b, &tm_b))) a.use_tma = 1;
   }
   void* params[] = {&a, &tm_a, &tm_b};
@@ -461,6 +515,8 @@ int ptx_create(ptx_plan** out, size_t ptheta, size_t nz, size_t n, size_t nscan,
   p->slots = nullptr;
   p->l2_window = 0;
   p->l2_hit = 0.f;
+  memset(p->tmc, 0, sizeof(p->tmc));
+  p->tmc_next = 0;
   p->reg_E = nullptr;
   p->reg_AT = nullptr;
   p->reg_uf = 0;
@@ -873,10 +929,10 @@ int ptx_vec_dai_yuan_reduce(const void* g, const void* g0, const void* d, size_t
   return PTX_OK;
 }
 
-int ptx_vec_dai_yuan_update(const void* g, void* g0, void* d, size_t n, const double* red, int first,
+int ptx_vec_dai_yuan_update(void* g, void* g0, void* d, size_t n, const double* red, int first,
                             void* stream) {
   if (!g || !g0 || !d || !red) return fail(PTX_EINVAL, "ptx_vec_dai_yuan_update: null array");
-  k_dy_update<<<vec_grid(n), 256, 0, (cudaStream_t)stream>>>((const float2*)g, (float2*)g0,
+  k_dy_update<<<vec_grid(n), 256, 0, (cudaStream_t)stream>>>((float2*)g, (float2*)g0,
                                                              (float2*)d, n, red, first);
   g_launches.fetch_add(1);
   CUDA_TRY(cudaGetLastError());
@@ -894,6 +950,36 @@ int ptx_vec_axpy(void* y, const void* x, size_t n, const float* alpha_dev, void*
 int ptx_vec_axpy_s(void* y, const void* x, size_t n, float alpha, void* stream) {
   if (!y || !x) return fail(PTX_EINVAL, "ptx_vec_axpy_s: null array");
   k_axpy_s<<<vec_grid(n), 256, 0, (cudaStream_t)stream>>>((float2*)y, (const float2*)x, n, alpha);
+  g_launches.fetch_add(1);
+  CUDA_TRY(cudaGetLastError());
+  return PTX_OK;
+}
+
+int ptx_vec_axpy_out(void* out, const void* y, const void* x, size_t n, float alpha, void* stream) {
+  if (!out || !y || !x) return fail(PTX_EINVAL, "ptx_vec_axpy_out: null array");
+  k_axpy_out<<<vec_grid(n), 256, 0, (cudaStream_t)stream>>>((float2*)out, (const float2*)y, (const float2*)x, n, alpha);
+  g_launches.fetch_add(1);
+  CUDA_TRY(cudaGetLastError());
+  return PTX_OK;
+}
+
+int ptx_vec_zero(void* x, size_t nbytes, void* stream) {
+  if (!x) return fail(PTX_EINVAL, "ptx_vec_zero: null array");
+  CUDA_TRY(cudaMemsetAsync(x, 0, nbytes, (cudaStream_t)stream));
+  return PTX_OK;
+}
+
+int ptx_cg_apply_shifts(float* scan, const double* shifts, size_t nscan, void* stream) {
+  if (!scan || !shifts) return fail(PTX_EINVAL, "ptx_cg_apply_shifts: null array");
+  k_apply_shifts<<<vec_grid(2 * nscan), 256, 0, (cudaStream_t)stream>>>(scan, shifts, 2 * nscan);
+  g_launches.fetch_add(1);
+  CUDA_TRY(cudaGetLastError());
+  return PTX_OK;
+}
+
+int ptx_cg_pick3(double* dst, const double* src, int i0, int i1, int i2, void* stream) {
+  if (!dst || !src || i0 < 0 || i1 < 0 || i2 < 0) return fail(PTX_EINVAL, "ptx_cg_pick3: bad argument");
+  k_pick3<<<1, 32, 0, (cudaStream_t)stream>>>(dst, src, i0, i1, i2);
   g_launches.fetch_add(1);
   CUDA_TRY(cudaGetLastError());
   return PTX_OK;

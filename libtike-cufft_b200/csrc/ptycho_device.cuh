@@ -357,7 +357,7 @@ __device__ __forceinline__ void patch_issue(Cta<P>& c, const CUtensorMap* tm, co
 }
 // near plane of block cb from the landed patch; ends with a block barrier (the tile is about to be
 // overwritten by the transform / the next patch)
-template <class P, bool FULL>
+template <class P, bool FULL, bool ONES = false>
 __device__ __forceinline__ void gather_tma_impl(float2 (&v)[P::E], Cta<P>& c, int cb, int shift,
                                                 const float2* __restrict__ prb, const Geo& g,
                                                 const Pat& p) {
@@ -370,7 +370,7 @@ __device__ __forceinline__ void gather_tma_impl(float2 (&v)[P::E], Cta<P>& c, in
     const int iy = FULL ? y : y - g.o, ix = FULL ? x : x - g.o;
     v[e] = make_float2(0.f, 0.f);
     if (FULL || ((unsigned)iy < (unsigned)g.P && (unsigned)ix < (unsigned)g.P))
-      v[e] = __ldg(prb + iy * g.P + ix);
+      v[e] = ONES ? make_float2(1.f, 0.f) : __ldg(prb + iy * g.P + ix);
   }
   mbar_wait(smem_u32(c.bar + 1), c.phase2);
   c.phase2 ^= 1;
@@ -389,14 +389,14 @@ __device__ __forceinline__ void gather_tma_impl(float2 (&v)[P::E], Cta<P>& c, in
   }
   __syncthreads();
 }
-template <class P>
+template <class P, bool ONES = false>
 __device__ __forceinline__ void gather_tma(float2 (&v)[P::E], Cta<P>& c, int cb, int shift,
                                            const float2* __restrict__ prb, const Geo& g,
                                            const Pat& p) {
   if (g.P == P::N)
-    gather_tma_impl<P, true>(v, c, cb, shift, prb, g, p);
+    gather_tma_impl<P, true, ONES>(v, c, cb, shift, prb, g, p);
   else
-    gather_tma_impl<P, false>(v, c, cb, shift, prb, g, p);
+    gather_tma_impl<P, false, ONES>(v, c, cb, shift, prb, g, p);
 }
 
 // barrier of the S1 <-> S2 exchange: only the XG2 threads that actually trade data (fft_tile.cuh)

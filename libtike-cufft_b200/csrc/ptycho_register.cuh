@@ -825,7 +825,20 @@ __global__ void __launch_bounds__(P::NT) k_register(const PassArgs a,
     } else {
       auto load_nat = [&](const float2* img, int cb, float2(&v)[P::E]) {
         if (MODE == 0) {
-          gather_ones<P>(v, c, cb, img, g, p);
+          if (Patch<P>::TMA && a.use_tma) {
+            // all-ones probe, object patch by tensor copy (block cb + 1 is in flight while block cb's
+            // taps are read): the plain four-tap gather was 18 % of this kernel's stalls at 256^2
+            const CUtensorMap* tm = img == src ? &tm_a : &tm_b;
+            if (cb == 0) {
+              __syncthreads();  // every thread is done with the tile
+              patch_issue<P>(c, tm, g, p, t, 0);
+            }
+            const int shift = c.pshift;
+            gather_tma<P, true>(v, c, cb, shift, nullptr, g, p);  // ends with a block barrier
+            if (cb + 1 < P::RC) patch_issue<P>(c, tm, g, p, t, cb + 1);
+          } else {
+            gather_ones<P>(v, c, cb, img, g, p);
+          }
         } else {
 #pragma unroll
           for (int e = 0; e < P::E; ++e) {

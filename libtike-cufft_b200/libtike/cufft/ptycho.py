@@ -349,6 +349,9 @@ class CGPtychoSolver(PtychoCuFFT):
     position_correction = True
     #: upsampling factor of the position correction (ptycho.py:401)
     position_upsample = 100
+    #: keep a copy of every position-correction step's shifts in `shift_log` (diagnostics; one device
+    #: copy per iteration, off in production)
+    log_shifts = False
     #: step candidates evaluated per fused line-search pass
     ls_candidates = 4
     #: keep F(psi, probe_k) of each gradient pass in HBM (8 N^2 B per pattern and mode) so that the
@@ -390,8 +393,10 @@ class CGPtychoSolver(PtychoCuFFT):
     def _scalars(self, *vals):
         return torch.tensor(vals, dtype=torch.float32, device="cuda")
 
-    def _intensity(self, psi, scan, probe, data, inten, model, iscale=None):
-        red = torch.zeros(3, dtype=torch.float64, device=psi.device)
+    def _intensity(self, psi, scan, probe, data, inten, model, iscale=None, red=None):
+        """`red`: 3 zeroed device doubles to accumulate into (allocated when not given)."""
+        if red is None:
+            red = torch.zeros(3, dtype=torch.float64, device=psi.device)
         sc = self._scalars(iscale) if iscale is not None else None
         check(lib.ptx_cg_intensity(self._h, _ptr(psi), _ptr(scan), _ptr(probe), probe.shape[1],
                                    _ptr(data), _ptr(inten) if inten is not None else None,
@@ -411,17 +416,23 @@ class CGPtychoSolver(PtychoCuFFT):
                               _ptr(far_out) if far_out is not None else None, current_stream()))
 
     def _line_search(self, obj_a, prb_a, nm_a, m_a, obj_b, prb_b, nm_b, m_b, npairs, scan, data,
-                     p1, model, far_a=None, want_ab=False, p23=None):
+                     p1, model, far_a=None, want_ab=False, p23=None, slots=None):
         """Fused line_search_sqr: evaluates `ls_candidates` halvings per pass (ptycho.py:272-281).
         `far_a`: [npairs, T,S,N,N] cached first far fields (see `_grad(far_out=...)`).
         `want_ab`: also reduce a = sum sqrt(I data), b = sum I for every candidate intensity; after
         the call `self._ls_ab` holds (a, b, cost) of the intensity at HALF the returned step -- the
         update the solver applies (ptycho.py:393, 461) -- or None when that candidate was not among
-        the ones evaluated in the deciding pass."""
+        the ones evaluated in the deciding pass.  `self._ls_ab_dev` then is (device cost buffer, index of
+        a, of b, of the cost) for a device-side hand-over (ptx_cg_pick3).
+        `slots`: [npass, 16] zeroed device doubles, one row per fused pass (allocated beyond that)."""
         K = int(self.ls_candidates)
         c0 = 0
         self._ls_begin()
         self._ls_ab = None
+        self._ls_ab_dev = None
+        npass = 0
+        if getattr(self, "_h_cost", None) is None:
+            self._h_cost = torch.empty(16, dtype=torch.float64).pin_memory()
 
         def done(step, c):
             self.ls_steps.append(step)
@@ -429,17 +440,24 @@ class CGPtychoSolver(PtychoCuFFT):
                 j = 0 if step == 0 else int(round(-np.log2(step))) - c0 + 2  # slot of step / 2
                 if 0 <= j <= 4:
                     self._ls_ab = (c[5 + j], c[10 + j], c[j])
+                    self._ls_ab_dev = (cost, 5 + j, 10 + j, j)
             return step
 
         while True:
-            cost = torch.zeros(16, dtype=torch.float64, device=obj_a.device)  # 5 costs (+ 5 a + 5 b)
+            # 5 costs (+ 5 a + 5 b) of this pass
+            cost = (slots[npass] if slots is not None and npass < slots.shape[0]
+                    else torch.zeros(16, dtype=torch.float64, device=obj_a.device))
+            npass += 1
             check(lib.ptx_cg_linesearch(self._h, _ptr(obj_a), _ptr(prb_a), nm_a, m_a, _ptr(obj_b),
                                         _ptr(prb_b), nm_b, m_b, npairs, _ptr(scan), _ptr(data),
                                         _ptr(p1) if p1 is not None else None,
                                         _ptr(far_a) if far_a is not None else None, model, c0, K,
                                         1 if want_ab else 0, _ptr(p23) if p23 is not None else None,
                                         _ptr(cost), current_stream()))
-            c = self._sum(cost).cpu().numpy()
+            # the one host read of a pass: pinned buffer, no pageable staging, no allocation
+            self._h_cost.copy_(self._sum(cost), non_blocking=True)
+            torch.cuda.current_stream().synchronize()
+            c = self._h_cost.numpy().copy()
             self.ls_log.append((c0, c[:1 + K].copy()))
             step = self._ls_decide(c0, c, K)
             if step is not None:
@@ -462,21 +480,26 @@ class CGPtychoSolver(PtychoCuFFT):
                 return 0
         return None
 
-    def _dai_yuan(self, grad, grad0, d, first):
-        red = torch.zeros(3, dtype=torch.float64, device=grad.device)
+    def _dai_yuan(self, grad, grad0, d, first, red=None, zero_grad=False):
+        """`red`: 3 zeroed device doubles; `zero_grad`: leave `grad` zeroed for the next pass to
+        accumulate into (saves the fill launch)."""
+        if red is None:
+            red = torch.zeros(3, dtype=torch.float64, device=grad.device)
         n = grad.numel()
         if not first:
             check(lib.ptx_vec_dai_yuan_reduce(_ptr(grad), _ptr(grad0), _ptr(d), n, _ptr(red),
                                               current_stream()))
             self._sum(red)
         check(lib.ptx_vec_dai_yuan_update(_ptr(grad), _ptr(grad0), _ptr(d), n, _ptr(red),
-                                          1 if first else 0, current_stream()))
+                                          (1 if first else 0) | (2 if zero_grad else 0), current_stream()))
 
     def _axpy(self, y, x, alpha):
         check(lib.ptx_vec_axpy_s(_ptr(y), _ptr(x), y.numel(), float(alpha), current_stream()))
 
-    def _absmax(self, x):
-        out = torch.zeros(1, dtype=torch.float32, device=x.device)
+    def _absmax(self, x, out=None):
+        """`out`: one zeroed device float (allocated when not given)."""
+        if out is None:
+            out = torch.zeros(1, dtype=torch.float32, device=x.device)
         if x.is_contiguous():
             check(lib.ptx_vec_absmax(_ptr(x), x.numel(), _ptr(out), current_stream()))
         else:  # probe[:, k] with ptheta > 1: one launch per angle, same accumulator
@@ -628,23 +651,44 @@ class CGPtychoSolver(PtychoCuFFT):
         sc_obj = torch.ones(3, dtype=torch.float32, device=dev)   # {fscale, iscale, gscale}, object pass
         sc_prb = torch.ones(3, dtype=torch.float32, device=dev)   # {1, 1, gscale}, probe pass
 
+        # Per-iteration device scalars live in ONE preallocated buffer that a single memset clears at
+        # the top of an iteration; every reduction of the iteration accumulates into its own slot, so
+        # the loop allocates nothing and launches no torch fill / clone / pageable copy.
+        LSP = 6                                     # fused line-search passes with a preallocated row
+        nd = 3 + 3 + 16 * LSP + M * (3 + 3 + 16 * LSP)
+        buf = torch.zeros(8 * nd + 4 * (2 * M), dtype=torch.uint8, device=dev)
+        ws = buf[:8 * nd].view(torch.float64)
+        wf = buf[8 * nd:].view(torch.float32)        # absmax slots: M for |probe_k|, M for |psi|
+        red_int, dy_obj = ws[0:3], ws[3:6]
+        ls_obj = ws[6:6 + 16 * LSP].view(LSP, 16)
+        o = 6 + 16 * LSP
+        per = 3 + 3 + 16 * LSP
+        red_prb = [ws[o + m * per:o + m * per + 3] for m in range(M)]
+        dy_prb = [ws[o + m * per + 3:o + m * per + 6] for m in range(M)]
+        ls_prb = [ws[o + m * per + 6:o + (m + 1) * per].view(LSP, 16) for m in range(M)]
+        red_carried = torch.zeros(3, dtype=torch.float64, device=dev)  # survives the memset
+        psi_new = torch.empty_like(psi) if self.position_correction else None
+        shifts = torch.empty((S, 2), dtype=torch.float64, device=dev) if self.position_correction else None
+        nbuf = buf.numel()
+
         print("# congujate gradient parameters\n"
               "iteration, step size object, step size probe, function min")  # csv column headers
         gammaprb = 0
-        carried = None
+        carried = False
         reuse = bool(self.reuse_line_search_sums) and recover_prb and (M == 1 or p23 is not None)
         self.history = []  # (iteration, step size object, step size probe) -- diagnostics only
         self.ls_log = []   # (first candidate exponent, [f(0), f(2^-c0), ...]) per fused pass
         self.ls_steps = []  # raw result of every line search, in call order (replayable by an instrumented subclass)
-        self.shift_log = []  # device [S,2] float64 shifts of every position-correction step
+        self.shift_log = []  # device [S,2] float64 shifts of every position-correction step (log_shifts)
         for i in range(piter):
+            check(lib.ptx_vec_zero(_ptr(buf), nbuf, current_stream()))
             # 1) object retrieval subproblem with fixed probes (ptycho.py:327-345).  a, b, the probe
             # rescaling and the gradient scalars stay on the device: no host round trip here
-            if carried is not None:  # a, b, cost of this very intensity, from the last line search
-                red = torch.tensor(carried, dtype=torch.float64, device=dev)
-                carried = None
+            if carried:  # a, b, cost of this very intensity were left on the device by the last line search
+                red = red_carried
+                carried = False
             else:
-                red = self._intensity(psi, scan, probe, data, inten, mdl)
+                red = self._intensity(psi, scan, probe, data, inten, mdl, red=red_int)
             check(lib.ptx_cg_prep_scale(_ptr(red), mdl, _ptr(s_dev), _ptr(sc_obj), current_stream()))
             check(lib.ptx_vec_scale(_ptr(probe), probe.numel(), _ptr(s_dev), current_stream()))
             if i % 32 == 0:  # cost of this iteration's absfpsi, printed below (ptycho.py:481-482)
@@ -654,34 +698,32 @@ class CGPtychoSolver(PtychoCuFFT):
                     fmin = s ** 2 * r[1] - 2.0 * s * r[0] + sum_data
                 else:
                     fmin = float(self._intensity(psi, scan, probe, data, None, mdl)[2])
-            # gradient (ptycho.py:346-363)
-            gradpsi.zero_()
+            # gradient (ptycho.py:346-363); gradpsi is zero here (initially, then left so by _dai_yuan)
             for k in range(M):
-                check(lib.ptx_cg_prep_gscale(_ptr(self._absmax(probe[:, k])), 1.0, _ptr(sc_obj),
+                check(lib.ptx_cg_prep_gscale(_ptr(self._absmax(probe[:, k], out=wf[k:k + 1])), 1.0, _ptr(sc_obj),
                                              current_stream()))
                 self._grad(0, psi, scan, probe, k, data, inten, 0, 0, 0, mdl, gradpsi, sc=sc_obj,
                            far_out=far[k] if far is not None else None)
             # Dai-Yuan direction (ptycho.py:364-372)
-            self._dai_yuan(gradpsi, gradpsi0, dpsi, i == 0)
+            self._dai_yuan(gradpsi, gradpsi0, dpsi, i == 0, red=dy_obj, zero_grad=True)
             # line search (ptycho.py:374-393)
             gammapsi = 0.5 * self._line_search(psi, probe, M, 0, dpsi, probe, M, 0, M, scan, data,
-                                               None, mdl, far_a=far)
+                                               None, mdl, far_a=far, slots=ls_obj)
             if self.position_correction and i > 0:
                 # position correction (ptycho.py:398-403): register the all-ones-probe far fields of
                 # psi and psi + gamma dpsi for angle 0 and move its scan positions -- the caller's
                 # scan array is updated in place, like the reference's
-                psi_new = psi.clone()
-                self._axpy(psi_new, dpsi, gammapsi)
+                check(lib.ptx_vec_axpy_out(_ptr(psi_new), _ptr(psi), _ptr(dpsi), psi.numel(), float(gammapsi),
+                                           current_stream()))
                 if self.comm is None or self.comm.rank == 0:  # angle 0 of the run lives on rank 0
-                    shifts = torch.empty((S, 2), dtype=torch.float64, device=dev)
-                    check(lib.ptx_cg_position_shifts(self._h, _ptr(psi), _ptr(psi_new), _ptr(scan),
-                                                     int(self.position_upsample), _ptr(shifts),
-                                                     current_stream()))
-                    if S == 1:  # the reference's shape[dim] == 1 loop (ptycho.py:243-245)
-                        shifts[0] = 0
-                    self.shift_log.append(shifts)
-                    scan[0] = (scan[0].double() + shifts).float()  # float32 += float64, as CuPy casts
-                psi = psi_new
+                    if S > 1:
+                        check(lib.ptx_cg_position_shifts(self._h, _ptr(psi), _ptr(psi_new), _ptr(scan),
+                                                         int(self.position_upsample), _ptr(shifts),
+                                                         current_stream()))
+                        check(lib.ptx_cg_apply_shifts(_ptr(scan), _ptr(shifts), S, current_stream()))
+                    if self.log_shifts:  # (a batch of ONE position gets zero shifts: ptycho.py:243-245)
+                        self.shift_log.append(shifts.clone() if S > 1 else torch.zeros_like(shifts))
+                psi, psi_new = psi_new, psi
             else:
                 # update psi (ptycho.py:405)
                 self._axpy(psi, dpsi, gammapsi)
@@ -690,26 +732,29 @@ class CGPtychoSolver(PtychoCuFFT):
                 for m in range(M):
                     # 2) probe retrieval subproblem with fixed object (ptycho.py:420-441)
                     if multi and not (m > 0 and p23 is not None):
-                        self._intensity(psi, scan, probe, data, inten, mdl)
+                        self._intensity(psi, scan, probe, data, inten, mdl, red=red_prb[m])
                     kg = (float(M) if mdl == 0 else 1.0) / S      # Q13: * nmodes only for gaussian
-                    check(lib.ptx_cg_prep_gscale(_ptr(self._absmax(psi)), kg, _ptr(sc_prb),
+                    check(lib.ptx_cg_prep_gscale(_ptr(self._absmax(psi, out=wf[M + m:M + m + 1])), kg, _ptr(sc_prb),
                                                  current_stream()))
-                    gradprb[m].zero_()
+                    # gradprb[m] is zero here (initially, then left so by _dai_yuan)
                     self._grad(1, psi, scan, probe, m, data, inten, 0, 0, 0, mdl, gradprb[m], P * P,
                                sc=sc_prb, far_out=far[m] if far is not None else None)
                     if self.comm is not None:
                         self.comm.probe_grad_(gradprb[m])
                     # Dai-Yuan direction (ptycho.py:442-450)
-                    self._dai_yuan(gradprb[m], gradprb0[m], dprb[m], i == 0)
+                    self._dai_yuan(gradprb[m], gradprb0[m], dprb[m], i == 0, red=dy_prb[m], zero_grad=True)
                     # line search (ptycho.py:451-461)
+                    last = m == M - 1
                     gammaprb = 0.5 * self._line_search(psi, probe, M, m, psi, dprb[m], 1, 0, 1,
                                                        scan, data, inten, mdl,
                                                        far_a=far[m] if far is not None else None,
-                                                       want_ab=reuse and m == M - 1, p23=p23)
+                                                       want_ab=reuse and last, p23=p23, slots=ls_prb[m])
                     # a, b, cost of the intensity the NEXT iteration opens with: only the last mode's
-                    carried = ([float(x) for x in self._ls_ab]
-                               if (reuse and m == M - 1 and self._ls_ab is not None) else None)
-                    if p23 is not None and (m + 1 < M or carried is not None):
+                    carried = bool(reuse and last and self._ls_ab_dev is not None)
+                    if carried:
+                        cbuf, ia, ib, ic = self._ls_ab_dev
+                        check(lib.ptx_cg_pick3(_ptr(red_carried), _ptr(cbuf), ia, ib, ic, current_stream()))
+                    if p23 is not None and (m + 1 < M or carried):
                         # the intensity mode m + 1 (or the next iteration) will start from
                         check(lib.ptx_cg_intensity_step(_ptr(inten), _ptr(p23), inten.numel(),
                                                         float(gammaprb), current_stream()))

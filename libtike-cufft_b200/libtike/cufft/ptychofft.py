@@ -47,6 +47,10 @@ SYMBOLS = [
     ("ptx_vec_dai_yuan_update", _i, [_vp, _vp, _vp, _sz, _dp, _i, _vp]),
     ("ptx_vec_axpy", _i, [_vp, _vp, _sz, _fp, _vp]),
     ("ptx_vec_axpy_s", _i, [_vp, _vp, _sz, ctypes.c_float, _vp]),
+    ("ptx_vec_axpy_out", _i, [_vp, _vp, _vp, _sz, ctypes.c_float, _vp]),
+    ("ptx_vec_zero", _i, [_vp, _sz, _vp]),
+    ("ptx_cg_apply_shifts", _i, [_fp, _dp, _sz, _vp]),
+    ("ptx_cg_pick3", _i, [_dp, _dp, _i, _i, _i, _vp]),
     ("ptx_cg_prep_scale", _i, [_dp, _i, _fp, _fp, _vp]),
     ("ptx_cg_prep_gscale", _i, [_fp, ctypes.c_double, _fp, _vp]),
     ("ptx_vec_scale", _i, [_vp, _sz, _fp, _vp]),

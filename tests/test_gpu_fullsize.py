@@ -264,12 +264,20 @@ def test_cg_full_size_vs_reference(name):
             ex.forced_steps = list(steps)
             exact = ex.run_batch(data, psi0, scan, prb0, piter=piter, model=model, recover_prb=True,
                                  verbose=False)
+        # ... and the reference does not reproduce itself here (unordered atomics): a second run of its
+        # own cuFFT path, same inputs and decisions, tells how far two "correct" fp32 runs lie apart
+        with ref_gpu.RefCGPtychoSolver(S, ndet, ndet, 1, nz, n) as ref2:
+            ref2.position_correction = True
+            ref2.forced_steps = list(steps)
+            want2 = ref2.run_batch(data, psi0, scan, prb0, piter=piter, model=model, recover_prb=True,
+                                   verbose=False)
         for k in ("psi", "probe"):
-            e_ref, e_got = rel_l2(want[k], exact[k]), rel_l2(got[k], exact[k])
-            print("   %s: reference vs f64 %.2e   fused vs f64 %.2e" % (k, e_ref, e_got))
+            e_ref = max(rel_l2(want[k], exact[k]), rel_l2(want2[k], exact[k]), rel_l2(want2[k], want[k]))
+            e_got = rel_l2(got[k], exact[k])
+            print("   %s: reference vs f64 %.2e / %.2e, reference vs its re-run %.2e; fused vs f64 %.2e" % (
+                k, rel_l2(want[k], exact[k]), rel_l2(want2[k], exact[k]), rel_l2(want2[k], want[k]), e_got))
             # factor 3 on a single draw: see tests/test_gpu_cg.py::_assert_parity for the measurements
             assert e_got < max(3 * e_ref, TOL_CG), (k, e_got, e_ref)
-
 
 def test_pipelined_kernel_parity_subprocess():
     """The opt-in warp-specialised 128^2 object-gradient kernel (PTX_PIPE=1, csrc/ptycho_pipe.cuh): the

@@ -141,6 +141,7 @@ def test_cg_with_position_correction_vs_oracle(model):
                     shift_log=log)
     with pt.CGPtychoSolver(side * side, ndet, ndet, 1, 200, 220) as slv:
         assert slv.position_correction  # the reference's behaviour is the default
+        slv.log_shifts = True
         d_scan = torch.from_numpy(scan.copy()).cuda()
         got = slv.run(torch.from_numpy(data).cuda(), torch.from_numpy(init).cuda(), d_scan,
                       torch.from_numpy(prb0.copy()).cuda(), 4, model=model, recover_prb=True)

@@ -17,6 +17,7 @@ def ReplaySolver(*args, **kwargs):
 
     class _Replay(pt.CGPtychoSolver):
         forced_steps = None
+        log_shifts = True  # the parity tests compare the position-correction shifts step by step
 
         def _ls_begin(self):
             self._forced = self.forced_steps.pop(0) if self.forced_steps else None
