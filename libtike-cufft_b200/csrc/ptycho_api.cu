@@ -403,7 +403,9 @@ static int launch(ptx_plan* p, int kid, PassArgs& a, cudaStream_t st) {
                         kid == K_GRADC_POIS_OBJ || kid == K_GRADC_POIS_PRB;
   const bool want = !grad_obj1 &&
                     (policy == 2 || (policy == 1 && (ls || inten || (ops->RC > 1 && (kid == K_FWD || grad_any)))));
-  const bool reg_tma = kid == K_REG_OBJ && ops->RC > 1 && policy != 0;  // position correction, N > 128
+  // position correction: object patches of both images by tensor copy (profiles/r02t_reg_probe.txt: 64^2
+  // 0.364 -> 0.311 ms, 128^2 0.416 -> 0.403 ms, 256^2 2.061 -> 1.812 ms per 1024 patterns; identical shifts)
+  const bool reg_tma = kid == K_REG_OBJ && policy != 0;
   if ((want || reg_tma) && kid != K_NEAR && kid != K_ADJ_OBJ && kid != K_ADJ_PRB &&
       (!reg_kernel(kid) || reg_tma) && a.psi) {
     const bool two = ls || reg_tma;

@@ -243,6 +243,7 @@ class PtychoCuFFT(ptychofft):
         chunk k is being reconstructed, and results are read back asynchronously.
         """
         assert probe.ndim == 4, "probe needs 4 dimensions, not %d" % probe.ndim
+        psi_in, probe_in = psi, probe  # staged from the caller's arrays (page-locked in place once)
         psi = psi.copy()
         probe = probe.copy()
         T = self.ptheta
@@ -256,9 +257,10 @@ class PtychoCuFFT(ptychofft):
             ids = slice(k * T, (k + 1) * T)
             with torch.cuda.stream(copy_stream):
                 dev = []
-                for x in (data, psi, scan, probe):
-                    h = _host_tensor(x[ids])
-                    dev.append((h if h.is_pinned() else h.pin_memory()).cuda(non_blocking=True))
+                for x in (data, psi_in, scan, probe_in):
+                    # large arrays are DMA'd straight from the caller's (page-locked) memory; small ones
+                    # (positions, probes) go as they are -- a pinned staging buffer would cost more
+                    dev.append(_host_tensor(x[ids]).cuda(non_blocking=True))
                 ev = torch.cuda.Event()
                 ev.record(copy_stream)
             for t in dev:  # allocated on copy_stream, consumed by kernels on `main`: keep the blocks
@@ -266,6 +268,9 @@ class PtychoCuFFT(ptychofft):
             return ids, dev, ev
 
         pending = []  # (ids, pinned psi, pinned probe, event) of results in flight
+        shp_psi, shp_prb = (T,) + tuple(psi.shape[1:]), (T,) + tuple(probe.shape[1:])
+        h_out = [(torch.empty(shp_psi, dtype=torch.complex64).pin_memory(),
+                  torch.empty(shp_prb, dtype=torch.complex64).pin_memory()) for _ in range(2)]
         nxt = stage(0)
         for k in range(nchunk):
             ids, (data_gpu, psi_gpu, scan_gpu, prb_gpu), ev = nxt
@@ -273,8 +278,7 @@ class PtychoCuFFT(ptychofft):
             if k + 1 < nchunk:
                 nxt = stage(k + 1)
             result = self.run(data_gpu, psi_gpu, scan_gpu, prb_gpu, **kwargs)
-            h_psi = torch.empty(result["psi"].shape, dtype=torch.complex64).pin_memory()
-            h_prb = torch.empty(result["probe"].shape, dtype=torch.complex64).pin_memory()
+            h_psi, h_prb = h_out[k % 2]  # (the buffer of chunk k - 2 has been drained below)
             h_psi.copy_(result["psi"], non_blocking=True)
             h_prb.copy_(result["probe"], non_blocking=True)
             done = torch.cuda.Event()
