@@ -61,6 +61,28 @@ __device__ __forceinline__ Pat make_pat(const float2* __restrict__ scan, int idx
   return p;
 }
 
+// A zero the compiler cannot see through.  ptxas hoists the (pure) bounds / window predicate arithmetic of a
+// rarely taken generic branch above the branch that selects it, where it costs the common path
+// instructions and registers (k_linesearch at 128^2: 18 k warp instructions per pattern and 400-700 B of
+// spills, profiles/r02v_ls128_regions.txt).  Adding this to a quantity every predicate of the slow
+// branch depends on (the window offset, the patch origin) ties that arithmetic to the branch.
+__device__ __forceinline__ int opaque_zero() {
+  int z;
+  asm volatile("mov.u32 %0, 0;" : "=r"(z));
+  return z;
+}
+__device__ __forceinline__ Geo tied(const Geo& g, int z) {
+  Geo r = g;
+  r.o += z;
+  return r;
+}
+__device__ __forceinline__ Pat tied(const Pat& p, int z) {
+  Pat r = p;
+  r.R += z;
+  r.C += z;
+  return r;
+}
+
 // Bilinear object patch value at probe pixel (iy, ix).  Outside the object the field is taken as 0
 // (the reference reads out of bounds there).
 template <bool INSIDE>
@@ -310,12 +332,15 @@ __device__ __forceinline__ void gather_nat(float2 (&v)[P::E], const Cta<P>& c, i
         return;
       }
     }
-    if (p.inside)
+    if (p.inside) {
       gather_impl<P, true, true>(v, c, cb, psi_t, prb, g, p);
-    else
-      gather_impl<P, true, false>(v, c, cb, psi_t, prb, g, p);
+    } else {
+      const int z = opaque_zero();
+      gather_impl<P, true, false>(v, c, cb, psi_t, prb, tied(g, z), tied(p, z));
+    }
   } else {
-    gather_impl<P, false, false>(v, c, cb, psi_t, prb, g, p);
+    const int z = opaque_zero();
+    gather_impl<P, false, false>(v, c, cb, psi_t, prb, tied(g, z), tied(p, z));
   }
 }
 
@@ -396,7 +421,7 @@ __device__ __forceinline__ void gather_tma(float2 (&v)[P::E], Cta<P>& c, int cb,
   if (g.P == P::N)
     gather_tma_impl<P, true, ONES>(v, c, cb, shift, prb, g, p);
   else
-    gather_tma_impl<P, false, ONES>(v, c, cb, shift, prb, g, p);
+    gather_tma_impl<P, false, ONES>(v, c, cb, shift, prb, tied(g, opaque_zero()), p);
 }
 
 // barrier of the S1 <-> S2 exchange: only the XG2 threads that actually trade data (fft_tile.cuh)
@@ -824,10 +849,12 @@ __device__ __forceinline__ void scatter_block(float2 (&v)[P::E], const Cta<P>& c
                                               const float2* __restrict__ prb, float scale,
                                               float2* __restrict__ grad_t, const Geo& g,
                                               const Pat& p, TileFree tile_free) {
-  if (g.P == P::N && p.inside)
+  if (g.P == P::N && p.inside) {
     scatter_impl<P, true>(v, c, cb, prb, scale, grad_t, g, p, tile_free);
-  else
-    scatter_impl<P, false>(v, c, cb, prb, scale, grad_t, g, p, tile_free);
+  } else {
+    const int z = opaque_zero();
+    scatter_impl<P, false>(v, c, cb, prb, scale, grad_t, tied(g, z), tied(p, z), tile_free);
+  }
 }
 
 // ---------------------------------------------------------------- probe adjoint
@@ -856,10 +883,12 @@ template <class P>
 __device__ __forceinline__ void pacc_add(float2 (&v)[P::E], const Cta<P>& c, int cb,
                                          const float2* __restrict__ psi_t, float scale,
                                          const Geo& g, const Pat& p) {
-  if (g.P == P::N && p.inside)
+  if (g.P == P::N && p.inside) {
     pacc_impl<P, true, true>(v, c, cb, psi_t, scale, g, p);
-  else
-    pacc_impl<P, false, false>(v, c, cb, psi_t, scale, g, p);
+  } else {
+    const int z = opaque_zero();
+    pacc_impl<P, false, false>(v, c, cb, psi_t, scale, tied(g, z), tied(p, z));
+  }
 }
 template <class P>
 __device__ __forceinline__ void pacc_zero(const Cta<P>& c) {

@@ -161,16 +161,11 @@ __device__ __forceinline__ void gather_any(float2 (&v)[P::E], Cta<P>& c, int cb,
     gather_tma<P>(v, c, cb, shift, prb, g, p);  // ends with a block barrier: the tile is free again
     if (cb + 1 < P::RC) patch_issue<P>(c, tm, g, p, t, cb + 1);
   } else {
-    // The plain-load path is the exception where tensor copies are the rule, but ptxas hoists its
-    // bounds / window predicate arithmetic (~18 k warp instructions per pattern at 128^2, ncu source page
-    // of k_linesearch) above this branch.  Tie it to a value only this branch defines.
-    int zero = 0;
-    if (Patch<P>::TMA) asm volatile("mov.u32 %0, 0;" : "=r"(zero));  // (512^2 has no tensor-copy path: nothing to protect)
-    Geo g2 = g;
-    g2.o += zero;
-    Pat p2 = p;
-    p2.R += zero;
-    p2.C += zero;
+    // the plain-load path is the exception where tensor copies are the rule: keep its predicate
+    // arithmetic inside this branch (opaque_zero, ptycho_device.cuh); 512^2 has no tensor-copy path
+    const int zero = Patch<P>::TMA ? opaque_zero() : 0;
+    const Geo g2 = tied(g, zero);
+    const Pat p2 = tied(p, zero);
     gather_nat<P>(v, c, cb, psi_t, prb, g2, p2);
   }
 }

@@ -747,10 +747,12 @@ __device__ __forceinline__ void gather_ones_impl(float2 (&v)[P::E], const Cta<P>
 template <class P>
 __device__ __forceinline__ void gather_ones(float2 (&v)[P::E], const Cta<P>& c, int cb,
                                             const float2* __restrict__ psi_t, const Geo& g, const Pat& p) {
-  if (p.inside)
+  if (p.inside) {
     gather_ones_impl<P, true>(v, c, cb, psi_t, g, p);
-  else
-    gather_ones_impl<P, false>(v, c, cb, psi_t, g, p);
+  } else {
+    const int z = opaque_zero();
+    gather_ones_impl<P, false>(v, c, cb, psi_t, tied(g, z), tied(p, z));
+  }
 }
 
 // MODE 0: far fields of two OBJECTS under an all-ones probe at the scan positions (ptycho.py:398-401)
