@@ -204,6 +204,17 @@ int ptx_cg_apply_shifts(float* scan, const double* shifts, size_t nscan, void* s
 /* dst[0..2] = src[i0], src[i1], src[i2]: a, b and cost of the accepted line-search candidate become the
  * sums the next iteration opens with (ptycho.py:342-343), without a host round trip */
 int ptx_cg_pick3(double* dst, const double* src, int i0, int i1, int i2, void* stream);
+/* Device-side decision of one fused line-search pass, so that the host does not have to wait for the costs
+ * before it queues what follows (ptycho.py:272-281, the `while f(...) > fp1` of line_search_sqr): the first of
+ * the kdec (0..4; 0 accepts nothing) candidates 2^-c0, 2^-(c0+1), ... whose cost cost_row[1+j] is not above cost_row[0] is
+ * accepted.  *half_step_dev = half that step (the update of ptycho.py:393, 461), or 0 when none was accepted
+ * -- the _dev updates below are then no-ops; cost_row[15] = the accepted index or -1, for the host to read
+ * later; carry (may be NULL) = {a, b, cost} of the intensity at the half step (cost_row[5+j+2], [10+j+2],
+ * [j+2]; needs ptx_cg_linesearch(ab = 1) and kdec <= 3), or {1, 1, 0} when none was accepted. */
+int ptx_cg_ls_decide(double* cost_row, int c0, int kdec, float* half_step_dev, double* carry, void* stream);
+/* ptx_vec_axpy_out / ptx_cg_intensity_step with the step read from device memory (see ptx_cg_ls_decide) */
+int ptx_vec_axpy_out_dev(void* out, const void* y, const void* x, size_t n, const float* alpha_dev, void* stream);
+int ptx_cg_intensity_step_dev(float* inten, const void* p23, size_t n, const float* step_dev, void* stream);
 /* CG scalars on the device, in the reference's float32 arithmetic (ptycho.py:342-351):
  *   red = {a, b} (doubles)  ->  *s_out = a/b ; sc[0] = fscale = b/a (gaussian) or 1 ; sc[1] = (a/b)^2 */
 int ptx_cg_prep_scale(const double* red, int model, float* s_out, float* sc, void* stream);

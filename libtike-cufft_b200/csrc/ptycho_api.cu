@@ -93,6 +93,41 @@ __global__ void k_pick3(double* __restrict__ dst, const double* __restrict__ src
   }
 }
 
+// Device-side decision of one fused line-search pass (ptycho.py:272-281): the first of the `kdec`
+// candidates 2^-c0, 2^-(c0+1), ... whose cost row[1+j] is not above row[0] = f(p1) is accepted.  The kernel
+// leaves HALF that step (the update the solver applies, ptycho.py:393, 461) in *gam -- 0 when none was
+// accepted, which turns the updates queued behind it into no-ops -- the accepted index (or -1) in row[15]
+// for the host to read whenever it gets there, and, when `carry` is given, the a, b, cost of the intensity
+// at the half step (row[5+j+2], row[10+j+2], row[j+2]) for the next iteration ({1, 1, 0} when nothing was
+// accepted: the probe rescaling that reads it is then a multiplication by one).
+__global__ void k_ls_decide(double* __restrict__ row, int c0, int kdec, float* __restrict__ gam,
+                            double* __restrict__ carry) {
+  if (threadIdx.x != 0) return;
+  int jj = -1;
+  for (int j = 0; j < kdec; j++)
+    if (!(row[1 + j] > row[0])) {
+      jj = j;
+      break;
+    }
+  row[15] = (double)jj;
+  *gam = jj >= 0 ? ldexpf(0.5f, -(c0 + jj)) : 0.f;
+  if (carry) {
+    carry[0] = jj >= 0 ? row[5 + jj + 2] : 1.0;
+    carry[1] = jj >= 0 ? row[10 + jj + 2] : 1.0;
+    carry[2] = jj >= 0 ? row[jj + 2] : 0.0;
+  }
+}
+
+__global__ void k_axpy_out_d(float2* __restrict__ out, const float2* __restrict__ y, const float2* __restrict__ x,
+                             size_t n, const float* alpha) {
+  const float al = *alpha;
+  for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n;
+       i += (size_t)gridDim.x * blockDim.x) {
+    const float2 a = y[i], b = x[i];
+    out[i] = make_float2(a.x + al * b.x, a.y + al * b.y);
+  }
+}
+
 __global__ void k_axpy(float2* __restrict__ y, const float2* __restrict__ x, size_t n,
                        const float* alpha) {
   const float al = *alpha;
@@ -146,6 +181,16 @@ __global__ void k_axpy_s(float2* __restrict__ y, const float2* __restrict__ x, s
 // the line search left behind (|t1 + g t2|^2 = |t1|^2 + g^2 |t2|^2 + 2 g Re(t1 conj t2))
 __global__ void k_inten_update(float* __restrict__ inten, const float2* __restrict__ p23, size_t n, float g) {
   const float g2 = g * g;
+  for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n;
+       i += (size_t)gridDim.x * blockDim.x) {
+    const float2 v = __ldcs(p23 + i);
+    inten[i] += g2 * v.x + g * v.y;
+  }
+}
+__global__ void k_inten_update_d(float* __restrict__ inten, const float2* __restrict__ p23, size_t n,
+                                 const float* gam) {
+  const float g = *gam, g2 = g * g;
+  if (g == 0.f) return;  // nothing accepted (yet): leave the map exactly as it is
   for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n;
        i += (size_t)gridDim.x * blockDim.x) {
     const float2 v = __ldcs(p23 + i);
@@ -916,6 +961,32 @@ static int vec_grid(size_t n) {
 int ptx_cg_intensity_step(float* inten, const void* p23, size_t n, float step, void* stream) {
   if (!inten || !p23) return fail(PTX_EINVAL, "ptx_cg_intensity_step: null array");
   k_inten_update<<<vec_grid(n), 256, 0, (cudaStream_t)stream>>>(inten, (const float2*)p23, n, step);
+  g_launches.fetch_add(1);
+  CUDA_TRY(cudaGetLastError());
+  return PTX_OK;
+}
+
+int ptx_cg_intensity_step_dev(float* inten, const void* p23, size_t n, const float* step_dev, void* stream) {
+  if (!inten || !p23 || !step_dev) return fail(PTX_EINVAL, "ptx_cg_intensity_step_dev: null array");
+  k_inten_update_d<<<vec_grid(n), 256, 0, (cudaStream_t)stream>>>(inten, (const float2*)p23, n, step_dev);
+  g_launches.fetch_add(1);
+  CUDA_TRY(cudaGetLastError());
+  return PTX_OK;
+}
+
+int ptx_cg_ls_decide(double* cost_row, int c0, int kdec, float* half_step_dev, double* carry, void* stream) {
+  if (!cost_row || !half_step_dev || c0 < 0 || kdec < 0 || kdec > 4)
+    return fail(PTX_EINVAL, "ptx_cg_ls_decide: bad argument");
+  k_ls_decide<<<1, 32, 0, (cudaStream_t)stream>>>(cost_row, c0, kdec, half_step_dev, carry);
+  g_launches.fetch_add(1);
+  CUDA_TRY(cudaGetLastError());
+  return PTX_OK;
+}
+
+int ptx_vec_axpy_out_dev(void* out, const void* y, const void* x, size_t n, const float* alpha_dev, void* stream) {
+  if (!out || !y || !x || !alpha_dev) return fail(PTX_EINVAL, "ptx_vec_axpy_out_dev: null array");
+  k_axpy_out_d<<<vec_grid(n), 256, 0, (cudaStream_t)stream>>>((float2*)out, (const float2*)y, (const float2*)x, n,
+                                                              alpha_dev);
   g_launches.fetch_add(1);
   CUDA_TRY(cudaGetLastError());
   return PTX_OK;

@@ -358,6 +358,13 @@ class CGPtychoSolver(PtychoCuFFT):
     log_shifts = False
     #: step candidates evaluated per fused line-search pass
     ls_candidates = 4
+    #: decide the first pass of every line search on the device and let the host read the outcome one
+    #: gradient pass later (see `run`); False = the host reads the costs of a pass before it queues
+    #: anything else (what an instrumented subclass that overrides `_ls_decide` needs)
+    device_line_search = True
+    #: queue work ahead of a device-decided search: "adaptive" = not for a search kind (object, probe
+    #: mode m) whose previous first pass accepted nothing; True = always; False = never
+    ls_run_ahead = "adaptive"
     #: keep F(psi, probe_k) of each gradient pass in HBM (8 N^2 B per pattern and mode) so that the
     #: line search that follows does not gather and transform it again
     cache_far_field = True
@@ -420,53 +427,92 @@ class CGPtychoSolver(PtychoCuFFT):
                               _ptr(far_out) if far_out is not None else None, current_stream()))
 
     def _line_search(self, obj_a, prb_a, nm_a, m_a, obj_b, prb_b, nm_b, m_b, npairs, scan, data,
-                     p1, model, far_a=None, want_ab=False, p23=None, slots=None):
+                     p1, model, far_a=None, want_ab=False, p23=None, slots=None, gam=None, carry=None):
         """Fused line_search_sqr: evaluates `ls_candidates` halvings per pass (ptycho.py:272-281).
         `far_a`: [npairs, T,S,N,N] cached first far fields (see `_grad(far_out=...)`).
         `want_ab`: also reduce a = sum sqrt(I data), b = sum I for every candidate intensity; after
         the call `self._ls_ab` holds (a, b, cost) of the intensity at HALF the returned step -- the
-        update the solver applies (ptycho.py:393, 461) -- or None when that candidate was not among
-        the ones evaluated in the deciding pass.  `self._ls_ab_dev` then is (device cost buffer, index of
-        a, of b, of the cost) for a device-side hand-over (ptx_cg_pick3).
-        `slots`: [npass, 16] zeroed device doubles, one row per fused pass (allocated beyond that)."""
+        update the solver applies (ptycho.py:393, 461).  `self._ls_ab_dev` then is (device cost buffer,
+        index of a, of b, of the cost) for a device-side hand-over (ptx_cg_pick3).  So that the half
+        step is always among the candidates of the deciding pass, a pass with `want_ab` decides on its
+        first K - 1 candidates only (the order in which steps are tried is unchanged).
+        `slots`: [npass, 16] zeroed device doubles, one row per fused pass (allocated beyond that).
+        `gam`: one device float.  When given, the first pass is decided ON THE DEVICE
+        (ptx_cg_ls_decide: half the accepted step -> gam, {a, b, cost} -> `carry`) and the call returns
+        at once with a function `finish() -> (step, refit)` instead of the step: the caller queues the
+        work that follows against `gam` and calls finish() when it needs the host-side value.
+        `refit` is True when no candidate of the first pass was accepted; finish() has then run the
+        remaining passes the host-driven way and `gam` / `carry` still hold the no-op values."""
         K = int(self.ls_candidates)
-        c0 = 0
+        kdec = K - 1 if want_ab else K
+        assert kdec >= 1
         self._ls_begin()
         self._ls_ab = None
         self._ls_ab_dev = None
-        npass = 0
+        npass = [0]
         if getattr(self, "_h_cost", None) is None:
             self._h_cost = torch.empty(16, dtype=torch.float64).pin_memory()
+            self._h_rows = torch.empty((4, 16), dtype=torch.float64).pin_memory()
+            self._h_row_ev = [torch.cuda.Event() for _ in range(4)]
+            self._h_row_i = 0
 
-        def done(step, c):
-            self.ls_steps.append(step)
-            if want_ab:
-                j = 0 if step == 0 else int(round(-np.log2(step))) - c0 + 2  # slot of step / 2
-                if 0 <= j <= 4:
-                    self._ls_ab = (c[5 + j], c[10 + j], c[j])
-                    self._ls_ab_dev = (cost, 5 + j, 10 + j, j)
-            return step
-
-        while True:
+        def one_pass(c0):
             # 5 costs (+ 5 a + 5 b) of this pass
-            cost = (slots[npass] if slots is not None and npass < slots.shape[0]
+            cost = (slots[npass[0]] if slots is not None and npass[0] < slots.shape[0]
                     else torch.zeros(16, dtype=torch.float64, device=obj_a.device))
-            npass += 1
+            npass[0] += 1
             check(lib.ptx_cg_linesearch(self._h, _ptr(obj_a), _ptr(prb_a), nm_a, m_a, _ptr(obj_b),
                                         _ptr(prb_b), nm_b, m_b, npairs, _ptr(scan), _ptr(data),
                                         _ptr(p1) if p1 is not None else None,
                                         _ptr(far_a) if far_a is not None else None, model, c0, K,
                                         1 if want_ab else 0, _ptr(p23) if p23 is not None else None,
                                         _ptr(cost), current_stream()))
-            # the one host read of a pass: pinned buffer, no pageable staging, no allocation
-            self._h_cost.copy_(self._sum(cost), non_blocking=True)
-            torch.cuda.current_stream().synchronize()
-            c = self._h_cost.numpy().copy()
-            self.ls_log.append((c0, c[:1 + K].copy()))
-            step = self._ls_decide(c0, c, K)
-            if step is not None:
-                return done(step, c)
-            c0 += K
+            return self._sum(cost)
+
+        def done(step, c, cost, c0):
+            self.ls_steps.append(step)
+            if want_ab:
+                j = 0 if step == 0 else int(round(-np.log2(step))) - c0 + 2  # slot of step / 2
+                if 0 <= j <= K:
+                    self._ls_ab = (c[5 + j], c[10 + j], c[j])
+                    self._ls_ab_dev = (cost, 5 + j, 10 + j, j)
+            return step
+
+        def host_loop(c0):
+            while True:
+                cost = one_pass(c0)
+                # the one host read of a pass: pinned buffer, no pageable staging, no allocation
+                self._h_cost.copy_(cost, non_blocking=True)
+                torch.cuda.current_stream().synchronize()
+                c = self._h_cost.numpy().copy()
+                self.ls_log.append((c0, c[:1 + K].copy()))
+                step = self._ls_decide(c0, c, kdec)
+                if step is not None:
+                    return done(step, c, cost, c0)
+                c0 += kdec
+
+        if gam is None:
+            return host_loop(0)
+        cost = one_pass(0)
+        check(lib.ptx_cg_ls_decide(_ptr(cost), 0, kdec, _ptr(gam), _ptr(carry) if carry is not None else None,
+                                   current_stream()))
+        # (at most one search is in flight at a time: four rotating rows are ample)
+        row = self._h_rows[self._h_row_i % 4]
+        landed = self._h_row_ev[self._h_row_i % 4]
+        self._h_row_i += 1
+        row.copy_(cost, non_blocking=True)
+        landed.record()
+
+        def finish():
+            landed.synchronize()
+            c = row.numpy().copy()
+            self.ls_log.append((0, c[:1 + K].copy()))
+            jj = int(c[15])
+            if jj >= 0:
+                return done(2.0 ** -jj, c, cost, 0), False
+            return host_loop(kdec), True
+
+        return finish
 
     def _ls_begin(self):
         """Called once per line search, before its first pass (a seam for instrumented subclasses)."""
@@ -677,101 +723,246 @@ class CGPtychoSolver(PtychoCuFFT):
 
         print("# congujate gradient parameters\n"
               "iteration, step size object, step size probe, function min")  # csv column headers
-        gammaprb = 0
-        carried = False
         reuse = bool(self.reuse_line_search_sums) and recover_prb and (M == 1 or p23 is not None)
         self.history = []  # (iteration, step size object, step size probe) -- diagnostics only
         self.ls_log = []   # (first candidate exponent, [f(0), f(2^-c0), ...]) per fused pass
         self.ls_steps = []  # raw result of every line search, in call order (replayable by an instrumented subclass)
         self.shift_log = []  # device [S,2] float64 shifts of every position-correction step (log_shifts)
-        for i in range(piter):
+        self.ls_refits = 0  # line searches whose first fused pass accepted nothing (device_line_search)
+
+        # Line searches are decided on the device (ptx_cg_ls_decide) and the updates behind them read the
+        # step from device memory, so the host never waits for a cost before it queues the next kernels.
+        # It looks at the outcome one gradient pass LATER (`settle`): by then the answer has long landed
+        # in pinned memory and the GPU has work queued.  What is queued ahead of that look is chosen so
+        # that it is harmless when the first pass accepted nothing (step 0: the updates are no-ops, the
+        # gradient computed from the unchanged state is thrown away and queued again after the remaining
+        # passes have run the host-driven way).  Where no such work exists the host settles at once.
+        dls = bool(self.device_line_search)
+        gam = torch.zeros(1 + M, dtype=torch.float32, device=dev)  # half steps: object, probe modes
+        gam_obj, gam_prb = gam[0:1], [gam[1 + m:2 + m] for m in range(M)]
+        probe_k = [probe[:, k] for k in range(M)]           # views made once, not once per launch
+        wf_prb, wf_psi = [wf[k:k + 1] for k in range(M)], [wf[M + m:M + m + 1] for m in range(M)]
+        gprb_m, gprb0_m, dprb_m = list(gradprb), list(gradprb0), list(dprb)
+        far_m = list(far) if far is not None else [None] * M
+        prb_tm = [[probe[t, m] for t in range(T)] for m in range(M)]
+        dprb_mt = [[dprb[m, t] for t in range(T)] for m in range(M)]
+        state = {"carried": False, "pending": None}
+        # a search kind (object, probe mode m) whose last first pass accepted nothing is not run ahead of:
+        # on problems whose steps are habitually below 2^-3 the discarded gradient would be pure loss
+        trust = [self.ls_run_ahead is not False] * (1 + M)
+
+        def learn(kind, refit):
+            if self.ls_run_ahead == "adaptive":
+                trust[kind] = not refit
+        recs = []  # per-iteration records still waiting for a step size
+
+        def emit():
+            while recs and recs[0]["gpsi"] is not None and recs[0]["gprb"] is not None:
+                r = recs.pop(0)
+                self.history.append((r["i"], r["gpsi"], r["gprb"]))
+                # check convergence (ptycho.py:474-482)
+                if r["i"] % 32 == 0:
+                    print("%4d, %.3e, %.3e, %.7e" % (r["i"], r["gpsi"], r["gprb"], r["fmin"]))
+
+        def settle(redo=None):
+            """Host-side end of the line search still in flight (if any): log it, and when its first
+            pass accepted nothing, apply the update with the step the remaining passes found (`fix`)
+            and queue the work that was issued ahead of this call again (`redo`)."""
+            if state["pending"] is None:
+                return
+            finish, fix = state["pending"]
+            state["pending"] = None
+            step, refit = finish()
+            self.ls_refits += int(refit)
+            fix(step, refit)
+            if refit and redo is not None:
+                redo()
+            emit()
+
+        def submit(finish, fix, speculate):
+            state["pending"] = (finish, fix)
+            if not speculate:
+                settle()
+
+        def open_object_pass():
+            """Top of an iteration up to the object gradient (ptycho.py:327-363)."""
             check(lib.ptx_vec_zero(_ptr(buf), nbuf, current_stream()))
             # 1) object retrieval subproblem with fixed probes (ptycho.py:327-345).  a, b, the probe
             # rescaling and the gradient scalars stay on the device: no host round trip here
-            if carried:  # a, b, cost of this very intensity were left on the device by the last line search
+            if state["carried"]:  # a, b, cost of this very intensity were left on the device by the last line search
                 red = red_carried
-                carried = False
             else:
                 red = self._intensity(psi, scan, probe, data, inten, mdl, red=red_int)
             check(lib.ptx_cg_prep_scale(_ptr(red), mdl, _ptr(s_dev), _ptr(sc_obj), current_stream()))
             check(lib.ptx_vec_scale(_ptr(probe), probe.numel(), _ptr(s_dev), current_stream()))
-            if i % 32 == 0:  # cost of this iteration's absfpsi, printed below (ptycho.py:481-482)
+            # gradient (ptycho.py:346-363); gradpsi is zero here (initially, then left so by _dai_yuan)
+            for k in range(M):
+                check(lib.ptx_cg_prep_gscale(_ptr(self._absmax(probe_k[k], out=wf_prb[k])), 1.0, _ptr(sc_obj),
+                                             current_stream()))
+                self._grad(0, psi, scan, probe, k, data, inten, 0, 0, 0, mdl, gradpsi, sc=sc_obj,
+                           far_out=far_m[k])
+            return red
+
+        def reopen_object_pass():
+            check(lib.ptx_vec_zero(_ptr(gradpsi), gradpsi.numel() * 8, current_stream()))
+            return open_object_pass()
+
+        def open_probe_pass(m):
+            """Probe subproblem of mode m up to its gradient (ptycho.py:420-441)."""
+            if multi and not (m > 0 and p23 is not None):
+                self._intensity(psi, scan, probe, data, inten, mdl, red=red_prb[m])
+            kg = (float(M) if mdl == 0 else 1.0) / S      # Q13: * nmodes only for gaussian
+            check(lib.ptx_cg_prep_gscale(_ptr(self._absmax(psi, out=wf_psi[m])), kg, _ptr(sc_prb),
+                                         current_stream()))
+            # gradprb[m] is zero here (initially, then left so by _dai_yuan)
+            self._grad(1, psi, scan, probe, m, data, inten, 0, 0, 0, mdl, gprb_m[m], P * P,
+                       sc=sc_prb, far_out=far_m[m])
+            if self.comm is not None:
+                self.comm.probe_grad_(gprb_m[m])
+
+        def reopen_probe_pass(m):
+            check(lib.ptx_vec_zero(_ptr(wf_psi[m]), 4, current_stream()))
+            check(lib.ptx_vec_zero(_ptr(gprb_m[m]), gprb_m[m].numel() * 8, current_stream()))
+            open_probe_pass(m)
+
+        def update_probe(m, g):
+            """probe[:, m] += g dprb[m] (ptycho.py:463); g a host value or one device float"""
+            for t in range(T):
+                if torch.is_tensor(g):
+                    check(lib.ptx_vec_axpy(_ptr(prb_tm[m][t]), _ptr(dprb_mt[m][t]), P * P, _ptr(g), current_stream()))
+                else:
+                    self._axpy(prb_tm[m][t], dprb_mt[m][t], g)
+
+        for i in range(piter):
+            rec = {"i": i, "gpsi": None, "gprb": None if recover_prb else 0, "fmin": None}
+            recs.append(rec)
+            red = open_object_pass()
+            if state["pending"] is not None:
+                # the probe line search of the previous iteration: `red` was queued ahead of its outcome
+                box = []
+                settle(lambda: box.append(reopen_object_pass()))
+                if box:
+                    red = box[0]
+            state["carried"] = False
+            if i % 32 == 0:  # cost of this iteration's absfpsi, printed by emit() (ptycho.py:481-482)
                 if mdl == 0:
                     r = red.cpu().numpy()
                     s = float(np.float32(np.float32(r[0]) / np.float32(r[1])))
-                    fmin = s ** 2 * r[1] - 2.0 * s * r[0] + sum_data
+                    rec["fmin"] = s ** 2 * r[1] - 2.0 * s * r[0] + sum_data
                 else:
-                    fmin = float(self._intensity(psi, scan, probe, data, None, mdl)[2])
-            # gradient (ptycho.py:346-363); gradpsi is zero here (initially, then left so by _dai_yuan)
-            for k in range(M):
-                check(lib.ptx_cg_prep_gscale(_ptr(self._absmax(probe[:, k], out=wf[k:k + 1])), 1.0, _ptr(sc_obj),
-                                             current_stream()))
-                self._grad(0, psi, scan, probe, k, data, inten, 0, 0, 0, mdl, gradpsi, sc=sc_obj,
-                           far_out=far[k] if far is not None else None)
+                    rec["fmin"] = float(self._intensity(psi, scan, probe, data, None, mdl)[2])
             # Dai-Yuan direction (ptycho.py:364-372)
             self._dai_yuan(gradpsi, gradpsi0, dpsi, i == 0, red=dy_obj, zero_grad=True)
             # line search (ptycho.py:374-393)
-            gammapsi = 0.5 * self._line_search(psi, probe, M, 0, dpsi, probe, M, 0, M, scan, data,
-                                               None, mdl, far_a=far, slots=ls_obj)
-            if self.position_correction and i > 0:
-                # position correction (ptycho.py:398-403): register the all-ones-probe far fields of
-                # psi and psi + gamma dpsi for angle 0 and move its scan positions -- the caller's
-                # scan array is updated in place, like the reference's
-                check(lib.ptx_vec_axpy_out(_ptr(psi_new), _ptr(psi), _ptr(dpsi), psi.numel(), float(gammapsi),
-                                           current_stream()))
-                if self.comm is None or self.comm.rank == 0:  # angle 0 of the run lives on rank 0
+            ls = self._line_search(psi, probe, M, 0, dpsi, probe, M, 0, M, scan, data, None, mdl,
+                                   far_a=far, slots=ls_obj, gam=gam_obj if dls else None)
+            correct = self.position_correction and i > 0
+            rank0 = self.comm is None or self.comm.rank == 0  # angle 0 of the run lives on rank 0
+
+            def propose(g, psi=psi, psi_new=psi_new):
+                # psi + gamma dpsi and its registration against psi (ptycho.py:398-402): nothing is
+                # overwritten, so this can be queued before the step is known to be final
+                if torch.is_tensor(g):
+                    check(lib.ptx_vec_axpy_out_dev(_ptr(psi_new), _ptr(psi), _ptr(dpsi), psi.numel(), _ptr(g),
+                                                   current_stream()))
+                else:
+                    check(lib.ptx_vec_axpy_out(_ptr(psi_new), _ptr(psi), _ptr(dpsi), psi.numel(), float(g),
+                                               current_stream()))
+                if rank0 and S > 1:
+                    check(lib.ptx_cg_position_shifts(self._h, _ptr(psi), _ptr(psi_new), _ptr(scan),
+                                                     int(self.position_upsample), _ptr(shifts),
+                                                     current_stream()))
+
+            if dls:
+                if correct:
+                    def fix(step, refit, rec=rec):
+                        rec["gpsi"] = 0.5 * step
+                        learn(0, refit)
+                    if trust[0]:
+                        propose(gam_obj)
+                        submit(ls, fix, True)
+                        settle(lambda rec=rec: propose(rec["gpsi"]))
+                    else:
+                        submit(ls, fix, False)
+                        propose(rec["gpsi"])
+                else:
+                    # update psi (ptycho.py:405)
+                    check(lib.ptx_vec_axpy(_ptr(psi), _ptr(dpsi), psi.numel(), _ptr(gam_obj), current_stream()))
+
+                    def fix(step, refit, rec=rec, psi=psi):
+                        rec["gpsi"] = 0.5 * step
+                        learn(0, refit)
+                        if refit:
+                            self._axpy(psi, dpsi, 0.5 * step)
+                    # the probe gradient that follows only reads psi; a new iteration would rescale the probe
+                    submit(ls, fix, recover_prb and trust[0])
+            else:
+                rec["gpsi"] = 0.5 * ls
+                if correct:
+                    propose(rec["gpsi"])
+                else:
+                    self._axpy(psi, dpsi, rec["gpsi"])
+            if correct:
+                # position correction (ptycho.py:398-403): the scan positions of angle 0 move by the shifts
+                # between psi and psi + gamma dpsi -- the caller's scan array is updated in place, like
+                # the reference's
+                if rank0:
                     if S > 1:
-                        check(lib.ptx_cg_position_shifts(self._h, _ptr(psi), _ptr(psi_new), _ptr(scan),
-                                                         int(self.position_upsample), _ptr(shifts),
-                                                         current_stream()))
                         check(lib.ptx_cg_apply_shifts(_ptr(scan), _ptr(shifts), S, current_stream()))
                     if self.log_shifts:  # (a batch of ONE position gets zero shifts: ptycho.py:243-245)
                         self.shift_log.append(shifts.clone() if S > 1 else torch.zeros_like(shifts))
                 psi, psi_new = psi_new, psi
-            else:
-                # update psi (ptycho.py:405)
-                self._axpy(psi, dpsi, gammapsi)
 
             if recover_prb:
                 for m in range(M):
                     # 2) probe retrieval subproblem with fixed object (ptycho.py:420-441)
-                    if multi and not (m > 0 and p23 is not None):
-                        self._intensity(psi, scan, probe, data, inten, mdl, red=red_prb[m])
-                    kg = (float(M) if mdl == 0 else 1.0) / S      # Q13: * nmodes only for gaussian
-                    check(lib.ptx_cg_prep_gscale(_ptr(self._absmax(psi, out=wf[M + m:M + m + 1])), kg, _ptr(sc_prb),
-                                                 current_stream()))
-                    # gradprb[m] is zero here (initially, then left so by _dai_yuan)
-                    self._grad(1, psi, scan, probe, m, data, inten, 0, 0, 0, mdl, gradprb[m], P * P,
-                               sc=sc_prb, far_out=far[m] if far is not None else None)
-                    if self.comm is not None:
-                        self.comm.probe_grad_(gradprb[m])
+                    open_probe_pass(m)
+                    settle(lambda m=m: reopen_probe_pass(m))
                     # Dai-Yuan direction (ptycho.py:442-450)
-                    self._dai_yuan(gradprb[m], gradprb0[m], dprb[m], i == 0, red=dy_prb[m], zero_grad=True)
+                    self._dai_yuan(gprb_m[m], gprb0_m[m], dprb_m[m], i == 0, red=dy_prb[m], zero_grad=True)
                     # line search (ptycho.py:451-461)
                     last = m == M - 1
-                    gammaprb = 0.5 * self._line_search(psi, probe, M, m, psi, dprb[m], 1, 0, 1,
-                                                       scan, data, inten, mdl,
-                                                       far_a=far[m] if far is not None else None,
-                                                       want_ab=reuse and last, p23=p23, slots=ls_prb[m])
-                    # a, b, cost of the intensity the NEXT iteration opens with: only the last mode's
-                    carried = bool(reuse and last and self._ls_ab_dev is not None)
-                    if carried:
-                        cbuf, ia, ib, ic = self._ls_ab_dev
-                        check(lib.ptx_cg_pick3(_ptr(red_carried), _ptr(cbuf), ia, ib, ic, current_stream()))
-                    if p23 is not None and (m + 1 < M or carried):
-                        # the intensity mode m + 1 (or the next iteration) will start from
-                        check(lib.ptx_cg_intensity_step(_ptr(inten), _ptr(p23), inten.numel(),
-                                                        float(gammaprb), current_stream()))
-                    # update probe (ptycho.py:463)
-                    if T == 1:
-                        self._axpy(probe[0, m], dprb[m, 0], gammaprb)
+                    want = reuse and last
+                    ls = self._line_search(psi, probe, M, m, psi, dprb_m[m], 1, 0, 1, scan, data, inten, mdl,
+                                           far_a=far_m[m],
+                                           want_ab=want, p23=p23, slots=ls_prb[m],
+                                           gam=gam_prb[m] if dls else None,
+                                           carry=red_carried if (dls and want) else None)
+
+                    def after_search(step, refit, m=m, last=last, want=want, rec=rec):
+                        """What the host does once a probe line search has a step it did not get on the device."""
+                        g = 0.5 * step
+                        if last:
+                            rec["gprb"] = g
+                        learn(1 + m, refit)
+                        if not refit:
+                            return
+                        # a, b, cost of the intensity the NEXT iteration opens with: only the last mode's
+                        state["carried"] = bool(want and self._ls_ab_dev is not None)
+                        if state["carried"]:
+                            cbuf, ia, ib, ic = self._ls_ab_dev
+                            check(lib.ptx_cg_pick3(_ptr(red_carried), _ptr(cbuf), ia, ib, ic, current_stream()))
+                        if p23 is not None and (m + 1 < M or state["carried"]):
+                            # the intensity mode m + 1 (or the next iteration) will start from
+                            check(lib.ptx_cg_intensity_step(_ptr(inten), _ptr(p23), inten.numel(), float(g),
+                                                            current_stream()))
+                        update_probe(m, g)
+
+                    if dls:
+                        g_dev = gam_prb[m]
+                        state["carried"] = want  # the device left a, b, cost in red_carried ({1, 1, 0} if it accepted nothing)
+                        if p23 is not None and (m + 1 < M or want):
+                            check(lib.ptx_cg_intensity_step_dev(_ptr(inten), _ptr(p23), inten.numel(), _ptr(g_dev),
+                                                                current_stream()))
+                        update_probe(m, g_dev)
+                        # ahead of the outcome: the next mode's gradient only reads the probe; a new iteration
+                        # rescales it, which is exact only with the device's {1, 1, 0} hand-over
+                        submit(ls, after_search, ((not last) or want) and trust[1 + m])
                     else:
-                        for t in range(T):
-                            self._axpy(probe[t, m], dprb[m, t], gammaprb)
-            self.history.append((i, gammapsi, gammaprb))
-            # check convergence (ptycho.py:474-482)
-            if i % 32 == 0:
-                print("%4d, %.3e, %.3e, %.7e" % (i, gammapsi, gammaprb, fmin))
+                        after_search(ls, True)
+            emit()
+        settle()
+        emit()
 
         if probe is not probe_in:
             probe_in.copy_(probe)

@@ -51,6 +51,9 @@ SYMBOLS = [
     ("ptx_vec_zero", _i, [_vp, _sz, _vp]),
     ("ptx_cg_apply_shifts", _i, [_fp, _dp, _sz, _vp]),
     ("ptx_cg_pick3", _i, [_dp, _dp, _i, _i, _i, _vp]),
+    ("ptx_cg_ls_decide", _i, [_dp, _i, _i, _fp, _dp, _vp]),
+    ("ptx_vec_axpy_out_dev", _i, [_vp, _vp, _vp, _sz, _fp, _vp]),
+    ("ptx_cg_intensity_step_dev", _i, [_fp, _vp, _sz, _fp, _vp]),
     ("ptx_cg_prep_scale", _i, [_dp, _i, _fp, _fp, _vp]),
     ("ptx_cg_prep_gscale", _i, [_fp, ctypes.c_double, _fp, _vp]),
     ("ptx_vec_scale", _i, [_vp, _sz, _fp, _vp]),
@@ -87,7 +90,10 @@ def check(rc):
 def current_stream():
     """cudaStream_t of torch's current stream (0 = legacy default, as the reference uses)."""
     import torch
-    return ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
+    try:  # the raw handle without building a torch.cuda.Stream object: this sits in front of every launch
+        return ctypes.c_void_p(torch._C._cuda_getCurrentRawStream(torch._C._cuda_getDevice()))
+    except AttributeError:
+        return ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
 
 
 def launch_count():

@@ -19,6 +19,11 @@ def ReplaySolver(*args, **kwargs):
         forced_steps = None
         log_shifts = True  # the parity tests compare the position-correction shifts step by step
 
+        @property
+        def device_line_search(self):
+            # replayed decisions are taken by `_ls_decide` on the host; free-running it is the product path
+            return self.forced_steps is None
+
         def _ls_begin(self):
             self._forced = self.forced_steps.pop(0) if self.forced_steps else None
 
