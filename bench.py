@@ -64,7 +64,7 @@ FP32_NOMINAL_TFLOPS = 148 * 128 * 2 * 1.965e9 / 1e12  # 74.4, SURVEY.md section 
 C4_ANGLES = 168
 REF_ANGLES = 21   # angles per step (and per call) of the reference arm
 E2E_ANGLES = 21   # host-array legs: at most this many angles per rank (5.6 GB of pinned data at c4)
-CG_ANGLES = 4     # e2e_cg / sharded CG: angles per rank
+CG_ANGLES = 8     # e2e_cg / sharded CG: angles per rank
 CG_ITERS = 8
 
 

@@ -28,6 +28,7 @@ Documented deviations from the reference (see DESIGN.md "Quirks"):
   Q9  `_batch` chunks by ptheta (identical at ptheta = 1, the only value the
       reference's helper is valid for).
 """
+import concurrent.futures
 import ctypes
 import warnings
 import weakref
@@ -244,14 +245,25 @@ class PtychoCuFFT(ptychofft):
         """
         assert probe.ndim == 4, "probe needs 4 dimensions, not %d" % probe.ndim
         psi_in, probe_in = psi, probe  # staged from the caller's arrays (page-locked in place once)
-        psi = psi.copy()
-        probe = probe.copy()
         T = self.ptheta
         nchunk = scan.shape[0] // T
         if nchunk == 0:
-            return {"psi": psi, "probe": probe}
+            return {"psi": psi.copy(), "probe": probe.copy()}
         copy_stream = torch.cuda.Stream()
         main = torch.cuda.current_stream()
+        device = torch.cuda.current_device()
+        # Host-side copies run on ONE worker thread, in order: first the copies of psi / probe the call
+        # returns (1.4 GB at 168 angles of 1024^2), then each chunk's results as they land -- the thread
+        # that queues kernels never stops to move host memory while the GPU has nothing queued.
+        out = {}
+
+        def copy_inputs():
+            torch.cuda.set_device(device)
+            out["psi"], out["probe"] = psi_in.copy(), probe_in.copy()
+
+        def drain(ids, h_psi, h_prb, landed, keep):
+            landed.synchronize()
+            out["psi"][ids], out["probe"][ids] = h_psi.numpy(), h_prb.numpy()
 
         def stage(k):
             ids = slice(k * T, (k + 1) * T)
@@ -267,31 +279,37 @@ class PtychoCuFFT(ptychofft):
                 t.record_stream(main)  # out of copy_stream's pool until main is done with them
             return ids, dev, ev
 
-        pending = []  # (ids, pinned psi, pinned probe, event) of results in flight
+        R = 3  # pinned result buffers in rotation (kept on the solver: pinning costs milliseconds)
         shp_psi, shp_prb = (T,) + tuple(psi.shape[1:]), (T,) + tuple(probe.shape[1:])
-        h_out = [(torch.empty(shp_psi, dtype=torch.complex64).pin_memory(),
-                  torch.empty(shp_prb, dtype=torch.complex64).pin_memory()) for _ in range(2)]
-        nxt = stage(0)
-        for k in range(nchunk):
-            ids, (data_gpu, psi_gpu, scan_gpu, prb_gpu), ev = nxt
-            main.wait_event(ev)
-            if k + 1 < nchunk:
-                nxt = stage(k + 1)
-            result = self.run(data_gpu, psi_gpu, scan_gpu, prb_gpu, **kwargs)
-            h_psi, h_prb = h_out[k % 2]  # (the buffer of chunk k - 2 has been drained below)
-            h_psi.copy_(result["psi"], non_blocking=True)
-            h_prb.copy_(result["probe"], non_blocking=True)
-            done = torch.cuda.Event()
-            done.record(main)
-            pending.append((ids, h_psi, h_prb, done, result))
-            while len(pending) > 1:  # drain all but the newest
-                i0, a, b, e, _ = pending.pop(0)
-                e.synchronize()
-                psi[i0], probe[i0] = a.numpy(), b.numpy()
-        for i0, a, b, e, _ in pending:
-            e.synchronize()
-            psi[i0], probe[i0] = a.numpy(), b.numpy()
-        return {"psi": psi, "probe": probe}
+        cache = getattr(self, "_h_out", None)
+        if cache is None or cache[0] != (shp_psi, shp_prb):
+            cache = ((shp_psi, shp_prb),
+                     [(torch.empty(shp_psi, dtype=torch.complex64).pin_memory(),
+                       torch.empty(shp_prb, dtype=torch.complex64).pin_memory()) for _ in range(R)])
+            self._h_out = cache
+        h_out = cache[1]
+        with concurrent.futures.ThreadPoolExecutor(max_workers=1) as worker:
+            jobs = [worker.submit(copy_inputs)]
+            drained = [None] * R
+            nxt = stage(0)
+            for k in range(nchunk):
+                ids, (data_gpu, psi_gpu, scan_gpu, prb_gpu), ev = nxt
+                main.wait_event(ev)
+                if k + 1 < nchunk:
+                    nxt = stage(k + 1)
+                result = self.run(data_gpu, psi_gpu, scan_gpu, prb_gpu, **kwargs)
+                if drained[k % R] is not None:
+                    drained[k % R].result()  # chunk k - R has left this buffer
+                h_psi, h_prb = h_out[k % R]
+                h_psi.copy_(result["psi"], non_blocking=True)
+                h_prb.copy_(result["probe"], non_blocking=True)
+                landed = torch.cuda.Event()
+                landed.record(main)
+                drained[k % R] = worker.submit(drain, ids, h_psi, h_prb, landed, result)
+                jobs.append(drained[k % R])
+            for j in jobs:
+                j.result()  # (re-raises what a job raised)
+        return {"psi": out["psi"], "probe": out["probe"]}
 
 
 _REG_PLANS = {}
