@@ -16,7 +16,7 @@
 //
 // B changes hands by two named barriers (bar.arrive / bar.sync, producer-consumer): the swap
 // "result(n-1) out, patch(n) in" is one in-place pass of the FFT warps over their own 32 positions.
-// Which side does the probe multiplies was decided by ncu's stall samples (profiles/r02e_pipe_v2_ncu.txt):
+// Which side does the probe multiplies was decided by ncu's stall samples (profiles/r02f_pipe_ncu.txt):
 // with them in the helper loops the FFT warps sat 61 % of their time at the hand-over barrier.
 // Registers: 640 threads x 96 = 61440 of the SM's 65536 (the transform core needs < 96, measured with
 // -Xptxas -v).  Shared memory: B (128 x 130 complex = 133 KB) + the exchange tile + twiddles.  To
