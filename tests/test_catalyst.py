@@ -67,6 +67,46 @@ def test_h5_reader_needs_h5py():
             PtychoDAO.h5_reader("/nonexistent/extracted_scan339.h5")
 
 
+def test_h5_reader_lines_on_an_in_memory_file(monkeypatch):
+    """h5py is absent from this image, so `PtychoDAO.h5_reader`'s own lines (test_rec_script.py:21-40:
+    the scan id parsed out of the file name, the dataset names, the attributes) are exercised through a
+    stand-in `h5py` module whose File is an in-memory mapping with `.attrs` -- the reader must hand
+    exactly those datasets to `from_arrays`."""
+    import sys
+    import types
+    from libtike.cufft.catalyst import PtychoDAO
+    fid, attrs = synthetic_file()
+    opened = []
+
+    class File(dict):
+        def __init__(self, name, mode):
+            assert mode == "r"
+            opened.append(name)
+            super().__init__({("/" + k): v for k, v in fid.items()})
+            self.attrs = dict(attrs)
+
+        def __getitem__(self, key):  # h5py resolves 'data' and '/data' alike
+            return super().__getitem__(key if key.startswith("/") else "/" + key)
+
+        def __enter__(self):
+            return self
+
+        def __exit__(self, *exc):
+            return False
+
+    monkeypatch.setitem(sys.modules, "h5py", types.SimpleNamespace(File=File))
+    name = "/data/run_12/extracted_scan339.h5"
+    dao = PtychoDAO.h5_reader(name, view_dims=(300, 200))
+    assert opened == [name]
+    assert dao.pid == 339  # the second-to-last number in the name; the last is the 5 of ".h5" (test_rec_script.py:36)
+    want = PtychoDAO.from_arrays(fid["data"], fid["positions_0"], fid["positions_1"], fid["initprobe"],
+                                 fid["recprobe"], attrs, pid=339, view_dims=(300, 200))
+    for a, b in ((dao.data, want.data), (dao.positions, want.positions), (dao.probes, want.probes)):
+        assert a.dtype == b.dtype and np.array_equal(a, b)
+    assert dao.rotation_angle == want.rotation_angle
+    assert PtychoDAO.h5_reader(name, pid=5, view_dims=(300, 200)).pid == 5
+
+
 @pytest.mark.gpu
 @pytest.mark.parametrize("ndet,shift", [(64, True), (128, True), (256, False)])
 def test_device_data_preparation_is_bit_identical(ndet, shift):
