@@ -454,25 +454,60 @@ def run_b200(args, world, rank, local):
         kavg = float(np.mean(kt))
     abytes, aflops = algorithmic_bytes(w, T), algorithmic_flops(w, T)
 
-    # ---- end to end through the host-array API: E angles of this rank's shard
+    # ---- end to end through the host-array API.  The sample is E angles per rank (world * E in all).
+    # This leg is bound by the host-to-device links, and on a multi-GPU box those are not alike when all
+    # GPUs copy at once (profiles/r02z_pcie8.txt: 23 GB/s on four GPUs, 35 GB/s on the other four), so for
+    # N > 1 the sample is split in proportion to each rank's measured link rate (libtike.cufft.dist).
     E = min(T, E2E_ANGLES)
-    host = {"data": data[:E].cpu().numpy(), "psi": psi[:E].cpu().numpy(),
-            "scan": w["scan"][:E], "probe": w["probe"][:E]}
+    counts, rates = [E] * world, None
+    if world > 1:
+        from libtike.cufft.dist import link_rates, weighted_counts
+        rates = link_rates()
+        counts = weighted_counts(world * E, rates)
+    if counts[rank] == E and counts == [E] * world:
+        host = {"data": data[:E].cpu().numpy(), "psi": psi[:E].cpu().numpy(),
+                "scan": w["scan"][:E], "probe": w["probe"][:E]}
+    else:
+        # global angles of the sample, in rank order; this rank takes its weighted block of them
+        sample = [shard(args.workload, world, r)[0] + k for r in range(world) for k in range(E)]
+        lo = sum(counts[:rank])
+        mine = sample[lo:lo + counts[rank]]
+        assert mine, "a rank with a measured link rate always gets at least one angle"
+        parts = {"data": [], "psi": [], "scan": [], "probe": []}
+        i = 0
+        while i < len(mine):  # contiguous runs of global angles
+            j = i
+            while j + 1 < len(mine) and mine[j + 1] == mine[j] + 1 and j + 1 - i < 8:
+                j += 1
+            wr = make_angles(args.workload, mine[i], j + 1 - i)
+            tr = [torch.from_numpy(wr[k]).to(dev) for k in ("psi", "scan", "probe")]
+            with pt.CGPtychoSolver(S, wr["nprb"], N, j + 1 - i, nz, n) as sr:
+                parts["data"].append(synth_data(sr, *tr).cpu().numpy())
+            parts["psi"].append(np.ones_like(wr["psi"]))
+            parts["scan"].append(wr["scan"])
+            parts["probe"].append(wr["probe"])
+            del tr
+            i = j + 1
+        host = {k: np.concatenate(v) for k, v in parts.items()}
+        del parts
     e2e = {}
+    esteps = max(2, args.steps // 4)
     with pt.CGPtychoSolver(S, w["nprb"], N, 1, nz, n) as s1:
         for kind in ("pinned", "pageable"):
             h = {k: (pinned(v) if kind == "pinned" else np.ascontiguousarray(v)) for k, v in host.items()}
 
             def e2e_step():
-                s1.grad_ptycho_batch(h["data"], h["psi"], h["scan"], h["probe"], model="gaussian")
-            dt = wall_steps(e2e_step, max(2, args.steps // 4), 1, world)
-            e2e[kind] = world * E * S * max(2, args.steps // 4) / dt
+                if h["scan"].shape[0]:
+                    s1.grad_ptycho_batch(h["data"], h["psi"], h["scan"], h["probe"], model="gaussian")
+            dt = wall_steps(e2e_step, esteps, 1, world)
+            e2e[kind] = world * E * S * esteps / dt
             del h
-    h2d = sum(v.nbytes for v in host.values())
-    d2h = host["psi"].nbytes
+    # bytes per step and rank, averaged over the ranks (every angle is the same size)
+    h2d = sum(v.nbytes for v in host.values()) // counts[rank] * E
+    d2h = host["psi"].nbytes // counts[rank] * E
 
     # ---- the reference's host entry point: run_batch (ptycho.py:135-162), angle-iterations/s
-    C = min(T, CG_ANGLES)
+    C = min(T, CG_ANGLES, min(counts))
     with pt.CGPtychoSolver(S, w["nprb"], N, 1, nz, n) as s1, quiet():
         hc = {k: v[:C] for k, v in host.items()}
         s1.run_batch(hc["data"][:1], hc["psi"][:1], hc["scan"][:1], hc["probe"][:1], piter=2,
@@ -558,7 +593,11 @@ def run_b200(args, world, rank, local):
         "e2e": {"value": e2e["pinned"], "unit": "patterns/s", "h2d_bytes_per_step": h2d,
                 "d2h_bytes_per_step": d2h, "pageable": e2e["pageable"],
                 "api": "CGPtychoSolver.grad_ptycho_batch (host arrays in, host gradient out, ptheta=1 chunks)",
-                "sample": "%d angles per GPU per step (value: pinned host arrays; pageable: plain NumPy)" % E},
+                "sample": "%d angles per GPU per step on average (value: pinned host arrays; pageable: plain NumPy)" % E,
+                "angles_per_rank": counts,
+                "link_gbs": ([round(r, 1) for r in rates] if rates else None),
+                "sharding": ("equal" if rates is None else
+                             "in proportion to each rank's host-to-device rate with all GPUs copying at once")},
         "e2e_cg": e2e_cg,
         "gpu_launches": int(launches),
         "roofline": {"bound": "fp32", "achieved": aflops / kavg / 1e12, "peak": FP32_NOMINAL_TFLOPS,

@@ -21,7 +21,7 @@ import numpy as np
 import torch
 import torch.distributed as dist
 
-__all__ = ["shard_angles", "run_batch_sharded", "ScalarComm", "bind_to_gpu"]
+__all__ = ["shard_angles", "weighted_counts", "link_rates", "run_batch_sharded", "ScalarComm", "bind_to_gpu"]
 
 
 def bind_to_gpu(local_rank):
@@ -52,12 +52,58 @@ def bind_to_gpu(local_rank):
     return None
 
 
-def shard_angles(ntheta, world, rank):
+def weighted_counts(ntheta, weights):
+    """Split `ntheta` angles over len(weights) ranks in proportion to `weights` (largest-remainder
+    rounding, ties to the lower rank): [count of rank 0, count of rank 1, ...], summing to ntheta."""
+    w = np.asarray(weights, dtype=np.float64)
+    if w.ndim != 1 or w.size == 0 or not np.all(np.isfinite(w)) or np.any(w < 0) or w.sum() <= 0:
+        raise ValueError("weights must be non-negative, finite and not all zero")
+    quota = ntheta * w / w.sum()
+    counts = np.floor(quota).astype(np.int64)
+    order = np.argsort(-(quota - counts), kind="stable")
+    counts[order[:ntheta - int(counts.sum())]] += 1
+    return [int(c) for c in counts]
+
+
+def shard_angles(ntheta, world, rank, weights=None):
     """Contiguous block of angles owned by `rank`: ceil(ntheta / world) each, the tail may be short
-    or empty (168 angles on 8 GPUs -> 21 each)."""
+    or empty (168 angles on 8 GPUs -> 21 each).  With `weights` (one per rank, e.g. `link_rates()`)
+    the blocks are sized in proportion to them instead: when the host-array entry points are bound
+    by the host-to-device links and those are not alike, equal shards finish with the slowest link."""
+    if weights is not None:
+        if len(weights) != world:
+            raise ValueError("one weight per rank")
+        counts = weighted_counts(ntheta, weights)
+        lo = sum(counts[:rank])
+        return slice(lo, lo + counts[rank])
     per = -(-ntheta // world)
     lo = min(rank * per, ntheta)
     return slice(lo, min(lo + per, ntheta))
+
+
+def link_rates(group=None, nbytes=64 << 20, reps=8):
+    """Host-to-device copy rate (GB/s) of every rank's GPU while ALL ranks copy at once, from pinned
+    memory: [rate of rank 0, rate of rank 1, ...], identical on every rank.  On a box whose GPUs share
+    PCIe switches or root ports unevenly these differ (measured on an 8 x B200 VM: 23 GB/s on four
+    GPUs, 35 GB/s on the other four, 55 GB/s for any one of them alone; profiles/r02z_pcie8.txt) --
+    the weights `shard_angles` / `run_batch_sharded` take."""
+    src = torch.empty(nbytes, dtype=torch.uint8).pin_memory()
+    dst = torch.empty(nbytes, dtype=torch.uint8, device="cuda")
+    dst.copy_(src, non_blocking=True)
+    torch.cuda.synchronize()
+    world = dist.get_world_size(group) if dist.is_initialized() else 1
+    if world > 1:
+        dist.barrier(group)
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(reps):
+        dst.copy_(src, non_blocking=True)
+    e1.record()
+    e1.synchronize()
+    rate = reps * nbytes / (e0.elapsed_time(e1) * 1e-3) / 1e9
+    if world == 1:
+        return [rate]
+    return [float(r) for r in _gather_object(rate, group)]
 
 
 def _gather_object(obj, group):
@@ -67,19 +113,19 @@ def _gather_object(obj, group):
     return out
 
 
-def run_batch_sharded(make_solver, data, psi, scan, probe, group=None, **kwargs):
+def run_batch_sharded(make_solver, data, psi, scan, probe, group=None, weights=None, **kwargs):
     """`run_batch` with the angle axis sharded over the ranks of `group`.
 
     make_solver(nangles) -> a context-manager solver exposing run_batch(data, psi, scan, probe,
     **kwargs) (normally `lambda n: CGPtychoSolver(nscan, nprb, ndet, 1, nz, n)`).  Every rank passes
     the FULL host arrays (or at least valid views of its own block) and receives the FULL result:
     {'psi': [ntheta, nz, n], 'probe': [ntheta, M, P, P]}.  Ranks with an empty block just take part
-    in the gather.
+    in the gather.  `weights`: one per rank (the same list on every rank), see `shard_angles`.
     """
     world = dist.get_world_size(group) if dist.is_initialized() else 1
     rank = dist.get_rank(group) if dist.is_initialized() else 0
     ntheta = scan.shape[0]
-    mine = shard_angles(ntheta, world, rank)
+    mine = shard_angles(ntheta, world, rank, weights)
     n_mine = mine.stop - mine.start
     if n_mine > 0:
         with make_solver(n_mine) as slv:

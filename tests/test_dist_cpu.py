@@ -37,6 +37,26 @@ def test_shard_angles_partition():
     assert [b.stop - b.start for b in [d.shard_angles(168, 8, r) for r in range(8)]] == [21] * 8
 
 
+def test_weighted_shards():
+    """Blocks sized in proportion to per-rank weights (link rates): still a partition of the angle
+    axis, largest-remainder rounding, zero weight = empty block."""
+    d = _load_dist_module()
+    rates = [23.3, 23.3, 23.3, 23.2, 35.5, 35.5, 35.5, 35.4]  # profiles/r02z_pcie8.txt
+    counts = d.weighted_counts(168, rates)
+    assert counts == [17, 17, 17, 17, 25, 25, 25, 25]
+    blocks = [d.shard_angles(168, 8, r, rates) for r in range(8)]
+    assert [i for b in blocks for i in range(b.start, b.stop)] == list(range(168))
+    assert [b.stop - b.start for b in blocks] == counts
+    assert d.weighted_counts(5, [1, 0, 1]) == [3, 0, 2]
+    assert d.weighted_counts(0, [1, 2]) == [0, 0]
+    assert d.weighted_counts(7, [1, 1]) == [4, 3]
+    for bad in ([], [0, 0], [1, -1], [float("nan"), 1]):
+        with pytest.raises(ValueError):
+            d.weighted_counts(4, bad)
+    with pytest.raises(ValueError):
+        d.shard_angles(4, 2, 0, [1, 1, 1])
+
+
 class _OracleSolver(object):
     """Stand-in with the solver's run_batch contract (ptycho.py:135-162), NumPy oracle inside."""
 
@@ -69,7 +89,7 @@ def _problem(ntheta):
     return data.astype(np.float32), np.ones_like(w["psi"]), w["scan"], w["probe"] * (0.9 + 0.1j)
 
 
-def _worker(rank, world, port, ntheta, q):
+def _worker(rank, world, port, ntheta, q, weights=None):
     os.environ["MASTER_ADDR"] = "127.0.0.1"
     os.environ["MASTER_PORT"] = str(port)
     dist.init_process_group("gloo", rank=rank, world_size=world)
@@ -77,7 +97,7 @@ def _worker(rank, world, port, ntheta, q):
         d = _load_dist_module()
         data, psi, scan, probe = _problem(ntheta)
         res = d.run_batch_sharded(_OracleSolver, data, psi, scan, probe.astype(np.complex64),
-                                  piter=2, model="gaussian", recover_prb=True)
+                                  weights=weights, piter=2, model="gaussian", recover_prb=True)
         comm = d.ScalarComm()
         s = comm.sum_(torch.tensor([1.0 + rank, 10.0], dtype=torch.float64))
         m = comm.max_(torch.tensor([float(rank)], dtype=torch.float32))
@@ -89,13 +109,13 @@ def _worker(rank, world, port, ntheta, q):
         dist.destroy_process_group()
 
 
-@pytest.mark.parametrize("ntheta", [3, 1])
-def test_run_batch_sharded_world2_gloo(ntheta):
-    """2 ranks, ragged split (2 + 1 angles; 1 + 0 angles) == the unsharded run."""
+@pytest.mark.parametrize("ntheta,weights", [(3, None), (1, None), (3, [1.0, 2.6])])
+def test_run_batch_sharded_world2_gloo(ntheta, weights):
+    """2 ranks, ragged split (2 + 1 angles; 1 + 0 angles; weighted 1 + 2) == the unsharded run."""
     ctx = mp.get_context("spawn")
     q = ctx.Queue()
-    port = 29600 + os.getpid() % 300 + ntheta
-    procs = [ctx.Process(target=_worker, args=(r, 2, port, ntheta, q)) for r in range(2)]
+    port = 29600 + os.getpid() % 300 + ntheta + (7 if weights else 0)
+    procs = [ctx.Process(target=_worker, args=(r, 2, port, ntheta, q, weights)) for r in range(2)]
     for p in procs:
         p.start()
     got = q.get(timeout=240)
