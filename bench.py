@@ -358,7 +358,6 @@ def scalarcomm_check(pt, world, rank):
     scalars), on ranks 0 and 1; returns the record on rank 0."""
     import torch.distributed as dist
     from libtike.cufft.dist import ScalarComm
-    from oracle import numpy_ptycho as O  # noqa: F401  (not used: the check is product vs product)
     w = workloads.synth_angles(2, 200, 220, 64, 64, 5, 1, seed0=11)
     dev = torch.device("cuda", torch.cuda.current_device())
     psi_t, scan, probe = (torch.from_numpy(w[k]).to(dev) for k in ("psi", "scan", "probe"))
