@@ -511,14 +511,17 @@ def run_b200(args, world, rank, local):
         hc = {k: v[:C] for k, v in host.items()}
         s1.run_batch(hc["data"][:1], hc["psi"][:1], hc["scan"][:1], hc["probe"][:1], piter=2,
                      recover_prb=True)
-        barrier(world)
-        t0 = time.perf_counter()
-        s1.run_batch(hc["data"], hc["psi"], hc["scan"], hc["probe"], piter=CG_ITERS, recover_prb=True)
-        barrier(world)
-        dt = max_over_ranks(time.perf_counter() - t0, world)
+        dt = None
+        for _ in range(2):  # best of two: a fresh box still pages code in from the image (100 ms stalls)
+            barrier(world)
+            t0 = time.perf_counter()
+            s1.run_batch(hc["data"], hc["psi"], hc["scan"], hc["probe"], piter=CG_ITERS, recover_prb=True)
+            barrier(world)
+            t1 = max_over_ranks(time.perf_counter() - t0, world)
+            dt = t1 if dt is None else min(dt, t1)
     e2e_cg = {"value": world * C * CG_ITERS / dt, "unit": "angle-iterations/s",
               "api": "CGPtychoSolver.run_batch(piter=%d, recover_prb=True), pageable host arrays" % CG_ITERS,
-              "sample": "%d angles per GPU" % C}
+              "sample": "%d angles per GPU, best of two calls" % C}
     del host
 
     # ---- CG iterations/s
@@ -696,12 +699,16 @@ def run_reference(args, world, rank, local):
         r1.position_correction = True   # unconditional in the reference (ptycho.py:398-403)
         r1.run_batch(hdata[:1], psi_h[:1], w["scan"][:1], w["probe"][:1], piter=2, recover_prb=True,
                      verbose=False)
-        torch.cuda.synchronize()
-        t0 = time.perf_counter()
-        r1.run_batch(hdata[:C], psi_h[:C], w["scan"][:C], w["probe"][:C], piter=CG_ITERS,
-                     recover_prb=True, verbose=False)
-        torch.cuda.synchronize()
-        e2e_cg = C * CG_ITERS / (time.perf_counter() - t0)
+        dt = None
+        for _ in range(2):  # best of two, like the other arm
+            torch.cuda.synchronize()
+            t0 = time.perf_counter()
+            r1.run_batch(hdata[:C], psi_h[:C], w["scan"][:C], w["probe"][:C], piter=CG_ITERS,
+                         recover_prb=True, verbose=False)
+            torch.cuda.synchronize()
+            t1 = time.perf_counter() - t0
+            dt = t1 if dt is None else min(dt, t1)
+        e2e_cg = C * CG_ITERS / dt
     cg = None
     if not args.no_cg:  # the reference's solver (cp -> torch restatement over its own operators)
         with ref_gpu.RefCGPtychoSolver(S, w["nprb"], N, 1, nz, n) as r1, quiet():
@@ -732,7 +739,7 @@ def run_reference(args, world, rank, local):
                  "e2e_cg": {"value": e2e_cg, "unit": "angle-iterations/s",
                             "api": "CGPtychoSolver.run_batch(piter=%d, recover_prb=True) restated over the "
                                    "reference's operators, pageable host arrays" % CG_ITERS,
-                            "sample": "%d angles" % C}})
+                            "sample": "%d angles, best of two calls" % C}})
     return base
 
 

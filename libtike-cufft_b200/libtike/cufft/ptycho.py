@@ -63,7 +63,7 @@ _HOST_REGISTERED = {}  # base address -> (nbytes, weakref.finalize)
 #: chunks are then DMA'd straight from the caller's memory instead of going through a staging copy
 HOST_REGISTER_MIN_BYTES = 8 << 20
 #: cap of torch's intra-op CPU thread pool while `run_batch` is in flight (restored afterwards)
-HOST_POOL_THREADS = 4
+HOST_POOL_THREADS = 1
 
 
 def _host_tensor(a):
@@ -290,9 +290,8 @@ class PtychoCuFFT(ptychofft):
                        torch.empty(shp_prb, dtype=torch.complex64).pin_memory()) for _ in range(R)])
             self._h_out = cache
         h_out = cache[1]
-        # torch's intra-op pool defaults to one thread per core; after any parallel region those threads
-        # spin and starve the two threads that matter here (the kernel-queueing one and the copy worker):
-        # measured 125 -> 187 angle-iterations/s at 256^2 with the pool capped (profiles/r02z_omp.txt)
+        # keep torch's intra-op CPU pool out of the way of the two threads that matter here (the one that
+        # queues kernels and the copy worker) while the batch is in flight
         pool_threads = torch.get_num_threads()
         if pool_threads > HOST_POOL_THREADS:
             torch.set_num_threads(HOST_POOL_THREADS)
