@@ -81,6 +81,7 @@ class ClockSampler(threading.Thread):
     def __init__(self, index):
         super().__init__(daemon=True)
         self.index, self.samples, self.reasons, self.max_mhz = index, [], set(), None
+        self.mem, self.power = [], []
         self._stop_evt = threading.Event()
         try:
             import pynvml
@@ -104,6 +105,12 @@ class ClockSampler(threading.Thread):
         while not self._stop_evt.is_set():
             try:
                 self.samples.append(nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM))
+                if len(self.samples) % 16 == 1:  # memory clock and power: what differs between two boxes
+                    try:                         # whose SM clocks read alike
+                        self.mem.append(nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_MEM))
+                        self.power.append(nv.nvmlDeviceGetPowerUsage(self.h) / 1000.0)
+                    except Exception:
+                        pass
                 r = nv.nvmlDeviceGetCurrentClocksEventReasons(self.h)
                 for bit, name in names.items():
                     if r & bit:
@@ -117,7 +124,9 @@ class ClockSampler(threading.Thread):
         self.join(timeout=2)
         s = self.samples
         return {"sm_mhz": float(np.median(s)) if s else None, "sm_max_mhz": self.max_mhz,
-                "reasons": sorted(self.reasons), "samples": len(s)}
+                "reasons": sorted(self.reasons), "samples": len(s),
+                "mem_mhz": float(np.median(self.mem)) if self.mem else None,
+                "power_w": float(np.median(self.power)) if self.power else None}
 
 
 def physical_gpu_index(local):
