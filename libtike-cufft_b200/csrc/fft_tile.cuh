@@ -250,10 +250,14 @@ struct W128_3 {  // free bits: x[6:2], y[6:3]; lanes = x4,x5,x2,x3,x6 (coalesced
     return j == 0 ? 4 : j == 1 ? 5 : j == 2 ? 2 : j == 3 ? 3 : j == 4 ? 6 : (1 * 16 + (j - 5 + 3));
   }
 };
+#ifndef PTX_MINB6
+#define PTX_MINB6 3
+#endif
+
 template <>
 struct Plan<7> {
   static constexpr int L = 7, N = 128, LX = 7, LY = 7, NX = 128, NY = 128, RC = 1, LC = 0;
-  static constexpr int E = 32, NT = NX * NY / E, NSTAGE = 3, WBITS = 9;
+  static constexpr int E = 32, NT = NX * NY / E, NSTAGE = 3, WBITS = 9, MINB = 1;
   using S0 = Stage<4, 3, 5, 2, 0, NoBatch, W128_1>;
   using S1 = Stage<2, 2, 2, 3, 0, NoBatch, W128_2>;
   using S2 = Stage<0, 2, 0, 2, 1, B128_3, W128_3>;
@@ -279,7 +283,7 @@ struct WP128_1 {  // stage 0: free bits x[3:0], y[4:0]; lanes x0..x3, y2; then y
 };
 struct Plan7P {
   static constexpr int L = 7, N = 128, LX = 7, LY = 7, NX = 128, NY = 128, RC = 1, LC = 0;
-  static constexpr int E = 32, NT = NX * NY / E, NSTAGE = 3, WBITS = 9;
+  static constexpr int E = 32, NT = NX * NY / E, NSTAGE = 3, WBITS = 9, MINB = 1;
   using S0 = Stage<4, 3, 5, 2, 0, NoBatch, WP128_1>;
   using S1 = Stage<2, 2, 2, 3, 0, NoBatch, W128_2>;
   using S2 = Stage<0, 2, 0, 2, 1, B128_3, W128_3>;
@@ -312,6 +316,11 @@ template <>
 struct Plan<6> {
   static constexpr int L = 6, N = 64, LX = 6, LY = 6, NX = 64, NY = 64, RC = 1, LC = 0;
   static constexpr int E = 32, NT = NX * NY / E, NSTAGE = 3, WBITS = 7;
+  // resident CTAs per SM the kernels are compiled for.  Without a bound ptxas takes 190 registers for the fused
+  // gradient and only 2 CTAs (8 warps) fit.  Measured on B200 (profiles/r02z_grad64_ncu.txt), 8192 patterns: 3 CTAs
+  // (170 registers) +9 ... +20 % on every pass; 4 CTAs (128 registers, spills) the same again on large batches but
+  // 1-2 patterns per CTA at the 1024 patterns of one CG angle, where 3 is the most even (CG 1440-1490 it/s).
+  static constexpr int MINB = PTX_MINB6;
   using S0 = Stage<3, 3, 4, 2, 0, NoBatch, W64_1>;
   using S1 = Stage<0, 3, 2, 2, 0, NoBatch, W64_2>;
   using S2 = Stage<0, 0, 0, 2, 3, B64_3, W64_3>;
@@ -340,7 +349,7 @@ struct W256_2 {  // active x[1:0], y[1:0]; lanes x5,x6,x7,x2,x3 (= frequency bit
 template <>
 struct Plan<8> {
   static constexpr int L = 8, N = 256, LX = 8, LY = 6, NX = 256, NY = 64, RC = 4, LC = 2;
-  static constexpr int E = 32, NT = NX * NY / E, NSTAGE = 3, WBITS = 9;
+  static constexpr int E = 32, NT = NX * NY / E, NSTAGE = 3, WBITS = 9, MINB = 1;
   using S0 = Stage<5, 3, 4, 2, 0, NoBatch, WBIG_0>;
   using S1 = Stage<2, 3, 2, 2, 0, NoBatch, W256_1>;
   using S2 = Stage<0, 2, 0, 2, 1, B256_2, W256_2>;
@@ -368,7 +377,7 @@ struct W512_2 {  // active x[1:0], y[1:0]; lanes x5..x8,x2 (= frequency bits 0..
 template <>
 struct Plan<9> {
   static constexpr int L = 9, N = 512, LX = 9, LY = 5, NX = 512, NY = 32, RC = 16, LC = 4;
-  static constexpr int E = 32, NT = NX * NY / E, NSTAGE = 3, WBITS = 9;
+  static constexpr int E = 32, NT = NX * NY / E, NSTAGE = 3, WBITS = 9, MINB = 1;
   using S0 = Stage<5, 4, 4, 1, 0, NoBatch, WBIG_0>;
   using S1 = Stage<2, 3, 2, 2, 0, NoBatch, W512_1>;
   using S2 = Stage<0, 2, 0, 2, 1, B512_2, W512_2>;

@@ -260,6 +260,7 @@ struct ptx_plan {
   const PlanOps* ops;
   bool freed;
   int device, num_sms, grid;
+  int grid_k[K_COUNT];  // per kernel: CTAs that are resident at once, at most `grid` (0 = not asked yet)
   float2* tw;
   // per-CTA scratch, one contiguous [grid][...] array per kind; stash and accp are allocated the
   // first time a kernel that uses them is launched (ensure_scratch)
@@ -413,7 +414,7 @@ static bool reg_kernel(int kid) { return kid == K_REG_OBJ || kid == K_REG_FOURIE
 static int launch(ptx_plan* p, int kid, PassArgs& a, cudaStream_t st) {
   const PlanOps* ops = p->ops;
   const int npat = a.g.T * a.g.S;
-  const int grid = npat < p->grid ? npat : p->grid;
+  int grid = npat < p->grid ? npat : p->grid;
   alignas(64) CUtensorMap tm_a, tm_b;
   memset(&tm_a, 0, sizeof(tm_a));
   memset(&tm_b, 0, sizeof(tm_b));
@@ -473,11 +474,24 @@ static int launch(ptx_plan* p, int kid, PassArgs& a, cudaStream_t st) {
   a.accp = need_accp ? p->accp : nullptr;
   cudaLaunchConfig_t cfg;
   memset(&cfg, 0, sizeof(cfg));
-  cfg.gridDim = dim3(grid);
   const bool pipe = kid >= K_PIPE_GAUSS && kid <= K_PIPEMC_POIS;
   cfg.blockDim = dim3(pipe ? ops->NT_pipe : ops->NT);
   cfg.dynamicSmemBytes = pipe ? ops->smem_bytes_pipe
                               : reg ? ops->smem_bytes_reg : nodata ? ops->smem_bytes_nodata : ops->smem_bytes;
+  // A persistent grid larger than what is resident at once only queues CTAs behind the first wave (the
+  // position-correction kernel of the 64^2 plan needs 166-250 registers: 2 CTAs per SM, not the plan's 4)
+  if (!p->grid_k[kid]) {
+    int occ = 0;
+    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, ops->kernels[kid], (int)cfg.blockDim.x,
+                                                      cfg.dynamicSmemBytes) != cudaSuccess || occ < 1) {
+      cudaGetLastError();
+      occ = 1;
+    }
+    const int fit = p->num_sms * occ;
+    p->grid_k[kid] = fit < p->grid ? fit : p->grid;
+  }
+  if (grid > p->grid_k[kid]) grid = p->grid_k[kid];
+  cfg.gridDim = dim3(grid);
   cfg.stream = st;
   cudaLaunchAttribute attr[1];
   if (p->l2_window) {  // keep the staging frames in the persisting part of L2; everything else streams

@@ -197,7 +197,7 @@ __device__ __forceinline__ void dp_next(const Cta<P>& c, const float* data, int 
 // API forward: g = FFT2(pad(kappa * prb * patch))                      (ptychofft.cu:60-73)
 // ------------------------------------------------------------------------------------------
 template <class P>
-__global__ void __launch_bounds__(P::NT) k_fwd(const PassArgs a, const __grid_constant__ CUtensorMap tm_a,
+__global__ void __launch_bounds__(P::NT, P::MINB) k_fwd(const PassArgs a, const __grid_constant__ CUtensorMap tm_a,
                                                const __grid_constant__ CUtensorMap tm_b) {
   extern __shared__ __align__(128) unsigned char smem_raw[];
   Cta<P> c;
@@ -229,7 +229,7 @@ __global__ void __launch_bounds__(P::NT) k_fwd(const PassArgs a, const __grid_co
 // order.  Integer work of the path (patch origin, window offset, skip rule) is checked bit-exactly
 // through it.
 template <class P>
-__global__ void __launch_bounds__(P::NT) k_nearplane(const PassArgs a,
+__global__ void __launch_bounds__(P::NT, P::MINB) k_nearplane(const PassArgs a,
                                                      const __grid_constant__ CUtensorMap tm_a,
                                                      const __grid_constant__ CUtensorMap tm_b) {
   extern __shared__ __align__(128) unsigned char smem_raw[];
@@ -263,7 +263,7 @@ __global__ void __launch_bounds__(P::NT) k_nearplane(const PassArgs a,
 // API adjoints: inverse FFT + object scatter (FLG 0) or probe reduction (FLG 1)  (ptychofft.cu:76-88)
 // ------------------------------------------------------------------------------------------
 template <class P, int FLG>
-__global__ void __launch_bounds__(P::NT) k_adj(const PassArgs a, const __grid_constant__ CUtensorMap tm_a,
+__global__ void __launch_bounds__(P::NT, P::MINB) k_adj(const PassArgs a, const __grid_constant__ CUtensorMap tm_a,
                                                const __grid_constant__ CUtensorMap tm_b) {
   extern __shared__ __align__(128) unsigned char smem_raw[];
   Cta<P> c;
@@ -382,7 +382,7 @@ __device__ __forceinline__ void intensity_body(Cta<P>& c, const PassArgs& a, con
   block_reduce_add<3, P::NT / 32>(acc, c.red, a.red, c.tid);
 }
 template <class P, int MODEL>
-__global__ void __launch_bounds__(P::NT) k_intensity(const PassArgs a,
+__global__ void __launch_bounds__(P::NT, P::MINB) k_intensity(const PassArgs a,
                                                      const __grid_constant__ CUtensorMap tm_a,
                                                      const __grid_constant__ CUtensorMap tm_b) {
   extern __shared__ __align__(128) unsigned char smem_raw[];
@@ -400,7 +400,7 @@ __global__ void __launch_bounds__(P::NT) k_intensity(const PassArgs a,
 // sc = {fscale, iscale, gscale}
 // ------------------------------------------------------------------------------------------
 template <class P, int MODEL, int WHAT, bool CACHE>
-__global__ void __launch_bounds__(P::NT) k_grad(const PassArgs a, const __grid_constant__ CUtensorMap tm_a,
+__global__ void __launch_bounds__(P::NT, P::MINB) k_grad(const PassArgs a, const __grid_constant__ CUtensorMap tm_a,
                                                 const __grid_constant__ CUtensorMap tm_b) {
   extern __shared__ __align__(128) unsigned char smem_raw[];
   Cta<P> c;
@@ -505,7 +505,7 @@ __global__ void __launch_bounds__(P::NT) k_grad(const PassArgs a, const __grid_c
 // The first far field of a pair is parked in thread-private scratch while the second is transformed.
 // ------------------------------------------------------------------------------------------
 template <class P, int MODEL, bool AB, bool CACHED>
-__global__ void __launch_bounds__(P::NT) k_linesearch(const PassArgs a,
+__global__ void __launch_bounds__(P::NT, P::MINB) k_linesearch(const PassArgs a,
                                                       const __grid_constant__ CUtensorMap tm_a,
                                                       const __grid_constant__ CUtensorMap tm_b) {
   extern __shared__ __align__(128) unsigned char smem_raw[];
