@@ -472,6 +472,8 @@ def run_b200(args, world, rank, local):
         from libtike.cufft.dist import link_rates, weighted_counts
         rates = link_rates()
         counts = weighted_counts(world * E, rates)
+        if min(counts) < 1:  # a link that measured (almost) nothing: fall back to equal shards
+            counts, rates = [E] * world, None
     if counts[rank] == E and counts == [E] * world:
         host = {"data": data[:E].cpu().numpy(), "psi": psi[:E].cpu().numpy(),
                 "scan": w["scan"][:E], "probe": w["probe"][:E]}
